@@ -1,0 +1,59 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads, exports every symbol the header declares,
+and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    import vectordb_b200
+    if not os.path.exists(vectordb_b200.library_path()):
+        from vectordb_b200.lib import build_library
+        build_library()
+    return vectordb_b200.load_library()
+
+
+def test_header_symbols_exported():
+    L = _lib()
+    hdr = open(os.path.join(ROOT, "include", "epsilla_b200.h")).read()
+    declared = sorted(set(re.findall(r"EPS_API[^;(]*?\b(eps_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 19
+    for name in declared:
+        assert hasattr(L, name), "symbol %s declared in include/epsilla_b200.h but not exported" % name
+    from vectordb_b200.lib import EXPORTS
+    assert sorted(EXPORTS) == declared
+
+
+def test_struct_layouts_match_header():
+    from vectordb_b200.lib import BuildParams, FilterNode, StatsStruct
+    assert C.sizeof(FilterNode) == 64
+    assert C.sizeof(StatsStruct) == 64
+    assert C.sizeof(BuildParams) == 40
+
+
+def test_no_cpu_fallback_without_gpu():
+    import vectordb_b200
+    L = _lib()
+    if L.eps_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(vectordb_b200.EpsError) as e:
+        vectordb_b200.Index("l2", 8, host_vectors=np.zeros((4, 8), np.float32))
+    assert e.value.code == 50001  # EPS_ERR_NO_DEVICE
+    from vectordb_b200.index import pair_distances
+    with pytest.raises(vectordb_b200.EpsError):
+        pair_distances("l2", np.zeros((1, 4), np.float32), np.zeros((1, 4), np.float32))
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never route through oracle/ (tier rule ③)."""
+    pkg = os.path.join(ROOT, "vectordb_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                src = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle" not in src.lower() or f == "__init__.py" and False, "%s mentions oracle" % f

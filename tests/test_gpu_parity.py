@@ -1,0 +1,260 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI
+(libepsilla_b200.so via vectordb_b200.Index); the checker is the oracle (oracle_port.c, and the compiled
+reference oracle/_ref/libepsilla_ref.so when it travelled) and the committed golden fixtures."""
+import numpy as np
+import pytest
+
+from helpers import assert_same_results, exact_topk, gen, recall
+
+pytestmark = pytest.mark.gpu
+METRICS = ("l2", "ip", "cosine")
+
+
+@pytest.fixture(scope="module")
+def vdb():
+    import vectordb_b200
+    L = vectordb_b200.load_library()
+    assert L.eps_device_count() > 0, "GPU tests need a CUDA device"
+    return vectordb_b200
+
+
+# ---- A1-A3, A14: distances and Normalize ---------------------------------------------------------------
+def test_pair_distances_match_oracle(vdb, port):
+    from vectordb_b200.index import pair_distances
+    rng = np.random.default_rng(11)
+    for d in (1, 2, 3, 4, 7, 32, 100, 128, 130, 768, 1536):
+        a = rng.standard_normal((64, d)).astype(np.float32)
+        b = rng.random((64, d), dtype=np.float32)
+        for m in METRICS:
+            got = pair_distances(m, a, b)
+            want = np.array([port.distance(m, a[i], b[i]) for i in range(64)], np.float32)
+            assert np.allclose(got, want, rtol=1e-4, atol=1e-6), (d, m, np.abs(got - want).max())
+
+
+def test_normalize_matches_oracle(vdb, port):
+    from vectordb_b200.index import normalize
+    rng = np.random.default_rng(12)
+    for d in (2, 4, 33, 768):
+        v = rng.standard_normal((8, d)).astype(np.float32)
+        got = normalize(v)
+        want = np.stack([port.normalize(x) for x in v])
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-7)
+
+
+# ---- A9/A11 brute-force branch: reference known answers ---------------------------------------------------
+def test_dense_vector_golden(vdb, golden):
+    g = golden["dense_vector"]
+    for m in METRICS:
+        ix = vdb.Index(m, 4, host_vectors=g["stored_" + m])
+        ix.sync_rows(5)
+        ix.set_attrs(g["attrs"], int(g["attr_stride"]), 5)
+        ids, ds, cnt, _ = ix.search(g["query_" + m], 100)
+        assert cnt[0] == 5 and np.array_equal(ids[0, :5], g["order_" + m])
+        assert np.allclose(ds[0, :5], g["dist_" + m], rtol=1e-4, atol=1e-7)
+        assert np.all(ids[0, 5:] == -1)
+        ids, ds, cnt, _ = ix.search(g["query_" + m], 100, filter_nodes=g["filter_nodes"])
+        assert cnt[0] == 2 and np.array_equal(ids[0, :2], g["filter_order_" + m])
+        ix.close()
+
+
+# ---- A4-A8 + tail merge: the reference's graph-path golden test ------------------------------------------
+def test_halfcircle_golden(vdb, golden):
+    g = golden["halfcircle"]
+    perm = g["perm"]
+    ix = vdb.Index("cosine", 2, host_vectors=g["vectors"])
+    ix.sync_rows(5000)
+    ix.set_graph(5000, g["offsets"], g["nbrs"].astype(np.int64), int(g["nav"]))
+    ix.config(500, 500)
+    ids, ds, cnt, st = ix.search(g["query"], 500)
+    assert cnt[0] == 500
+    assert np.array_equal(perm[ids[0]], np.sort(perm[:5000])[:500]), "exact top-500 (db_server.cpp:1164-1181)"
+    assert_same_results(ids, ds, cnt, g["ids1"][None], g["d1"][None], [500], "halfcircle phase 1")
+    ix.sync_rows(10000)  # 5000 indexed + 5000 unindexed -> graph + brute-force tail merge
+    ids, ds, cnt, st = ix.search(g["query"], 500)
+    assert cnt[0] == 500
+    assert np.array_equal(perm[ids[0]], np.arange(500)), "graph + tail (db_server.cpp:1185-1200)"
+    assert_same_results(ids, ds, cnt, g["ids2"][None], g["d2"][None], [500], "halfcircle phase 2")
+    ix.close()
+
+
+# ---- every Search() mode against outputs of the reference itself ------------------------------------------
+@pytest.mark.parametrize("m", METRICS)
+def test_rand2k_all_modes(vdb, golden, m):
+    g = golden["rand2k"]
+    n, tail = 2000, 300
+    ix = vdb.Index(m, 32, host_vectors=g["stored_" + m])
+    ix.set_attrs(g["attrs"], int(g["attr_stride"]), n + tail)
+    nf = len(g["filters"])
+    rates = []
+
+    def check(tag, limit):
+        for fi in range(nf):
+            ids, ds, cnt, st = ix.search(g["queries_" + m], limit, filter_nodes=g["nodes_%d" % fi])
+            key = "%s_%s_f%d_" % (m, tag, fi)
+            rates.append(assert_same_results(ids, ds, cnt, g[key + "ids"], g[key + "dists"], g[key + "counts"], key))
+            if tag.startswith("graph"):
+                assert st["n_dist"] == int(g[key + "ndist"].sum()) or abs(st["n_dist"] - int(g[key + "ndist"].sum())) < 0.02 * st["n_dist"], key
+
+    # brute-force branch (no graph)
+    ix.sync_rows(400)
+    check("brute10", 10)
+    ix.sync_rows(n)
+    ix.set_graph(n, g["offsets_" + m], g["nbrs_" + m].astype(np.int64), int(g["nav_" + m]))
+    ix.config(500, 500)
+    check("graph10", 10)
+    if m == "l2":
+        check("graph100", 100)
+        ix.config(64, 64)
+        check("graphL64", 10)
+        ix.config(500, 500)
+        ix.set_deleted(g["deleted"])
+        check("del10", 10)
+        ix.sync_rows(n + tail)
+        check("tail10", 10)
+        check("tail100", 100)
+        ix.config(500, 500, prefilter=True)
+        check("pre10", 10)
+    ix.close()
+    assert np.mean(rates) > 0.9, "exact-match rate %.3f" % np.mean(rates)
+
+
+# ---- same graph, GPU search vs oracle search, bigger table ------------------------------------------------
+def test_graph_search_vs_port_same_graph(vdb, port):
+    n, d, nq = 20000, 64, 48
+    X, Q = gen(n, d, 101, "cluster"), gen(nq, d, 102, "cluster")
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.build(n)
+    ni, off, nb, nav = ix.get_graph()
+    assert ni == n and off[-1] == len(nb) and 0 <= nav < n
+    deg = np.diff(off)
+    assert deg.min() >= 1 and np.percentile(deg, 99) <= 64
+    for L, limit in ((500, 10), (128, 100)):
+        ix.config(L, L)
+        ids, ds, cnt, st = ix.search(Q, limit)
+        pids, pds, pcnt, pst = port.search_batch(metric="l2", vectors=X, queries=Q, limit=limit, n_indexed=n, offsets=off,
+                                                 nbrs=nb, nav=nav, L=L)
+        rate = assert_same_results(ids, ds, cnt, pids, pds, pcnt, "L=%d" % L)
+        assert rate > 0.9
+        assert abs(st["n_dist"] - pst[0]) <= 0.01 * pst[0]
+        assert abs(st["n_expand"] - pst[1]) <= 0.01 * pst[1]
+    truth = exact_topk(X, Q, 10)
+    ix.config(500, 500)
+    ids, _, _, _ = ix.search(Q, 10)
+    assert recall(ids, truth, 10) >= 0.98
+    # idempotence (visited bitmaps are left clean) and sortedness
+    ids2, ds2, _, _ = ix.search(Q, 10)
+    assert np.array_equal(ids, ids2)
+    assert np.all(np.diff(ds2, axis=1) >= 0)
+    ix.close()
+
+
+def test_reference_executor_on_gpu_built_graph(vdb, have_ref):
+    """The unmodified reference VecSearchExecutor searching the GPU-built CSR."""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libepsilla_ref.so did not travel")
+    from oracle.oracle import Ref
+    n, d, nq = 6000, 32, 24
+    X, Q = gen(n, d, 7), gen(nq, d, 8)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.build(n)
+    ni, off, nb, nav = ix.get_graph()
+    ix.config(500, 500)
+    ids, ds, cnt, _ = ix.search(Q, 10)
+    r = Ref("l2", d, n, [("ID", "int4")])
+    r.set_rows(X)
+    r.set_graph(ni, off, nb, nav)
+    r.make_executors(1, 1, 500)
+    rids, rds, rcnt = r.search_batch(Q, 10)
+    assert_same_results(ids, ds, cnt, rids, rds, rcnt, "reference executor")
+    ix.close()
+
+
+# ---- brute force: batched tile kernel and row kernel, all metrics, ragged dims ----------------------------
+@pytest.mark.parametrize("m", METRICS)
+def test_brute_force_batched(vdb, port, m):
+    for n, d, nq, k in ((30000, 128, 64, 10), (5000, 33, 3, 100), (1000, 6, 40, 500), (513, 768, 17, 10)):
+        X, Q = gen(n, d, n + d), gen(nq, d, n + d + 1)
+        ix = vdb.Index(m, d, host_vectors=X)
+        ix.sync_rows(n)
+        ix.config(500, 500, force_brute=True)
+        ids, ds, cnt, st = ix.search(Q, k)
+        sub = slice(0, min(nq, 6))
+        pids, pds, pcnt, _ = port.search_batch(metric=m, vectors=X, queries=Q[sub], limit=k, L=max(500, k), prefilter=True)
+        assert_same_results(ids[sub], ds[sub], cnt[sub], pids, pds, pcnt, "bf %s %dx%d" % (m, n, d))
+        assert st["n_dist"] == n * nq
+        truth = exact_topk(X, Q, min(k, 10), m)
+        assert recall(ids, truth, min(k, 10)) > 0.999
+        ix.close()
+
+
+def test_empty_and_edge_cases(vdb):
+    X = gen(10, 8, 1)
+    ix = vdb.Index("l2", 8, host_vectors=X, capacity=10)
+    ids, ds, cnt, _ = ix.search(X[0], 5)  # zero rows mirrored
+    assert cnt[0] == 0 and np.all(ids == -1) and np.all(np.isinf(ds))
+    ix.sync_rows(3)
+    ids, ds, cnt, _ = ix.search(X[:2], 5)  # fewer rows than limit
+    assert list(cnt) == [3, 3] and ids[0, 0] == 0 and ids[1, 0] == 1 and np.all(ids[:, 3:] == -1)
+    bits = np.zeros(2, np.uint8)
+    bits[0] = 0b111
+    ix.set_deleted(bits)  # everything deleted
+    ids, ds, cnt, _ = ix.search(X[0], 5)
+    assert cnt[0] == 0
+    with pytest.raises(vdb.EpsError):
+        ix.search(X[0], 5, filter_nodes=np.array([[2, 0, -1, -1, 0, 0, 0, -1]], np.int64))  # StringConst: out of scope
+    ix.close()
+
+
+# ---- build quality vs the reference-built graph on the same data -----------------------------------------
+def test_build_quality_vs_reference_graph(vdb, golden):
+    g = golden["rand2k"]
+    X, Q = g["stored_l2"][:2000], g["queries_l2"]
+    truth = exact_topk(X, Q, 10)
+    ix = vdb.Index("l2", 32, host_vectors=X)
+    ix.sync_rows(2000)
+    out = {}
+    for name in ("ref", "gpu"):
+        if name == "ref":
+            ix.set_graph(2000, g["offsets_l2"], g["nbrs_l2"].astype(np.int64), int(g["nav_l2"]))
+        else:
+            ix.build(2000)
+        for L in (64, 500):
+            ix.config(L, L)
+            ids, _, _, st = ix.search(Q, 10)
+            out[(name, L)] = (recall(ids, truth, 10), st["n_dist"] / len(Q))
+    for L in (64, 500):
+        assert out[("gpu", L)][0] >= out[("ref", L)][0] - 0.03, out
+        assert out[("gpu", L)][1] <= 1.5 * out[("ref", L)][1], out
+    ix.close()
+
+
+# ---- device-pointer API and the shard merge (multi-GPU exchange step) -------------------------------------
+def test_device_api_and_shard_merge(vdb):
+    import torch
+    from vectordb_b200.index import merge_shards_device
+    n, d, nq, k, S = 9000, 48, 32, 10, 3
+    X, Q = gen(n, d, 21), gen(nq, d, 22)
+    tq = torch.from_numpy(Q).cuda()
+    per = n // S
+    all_ids = torch.empty((S, nq, k), dtype=torch.int64, device="cuda")
+    all_d = torch.empty((S, nq, k), dtype=torch.float32, device="cuda")
+    cnts = torch.empty((nq,), dtype=torch.int64, device="cuda")
+    keep = []
+    for s in range(S):
+        ix = vdb.Index("l2", d, host_vectors=X[s * per:(s + 1) * per])
+        ix.sync_rows(per)
+        ix.config(500, 500, force_brute=True)
+        ix.search_device(tq.data_ptr(), nq, k, all_ids[s].data_ptr(), all_d[s].data_ptr(), cnts.data_ptr())
+        all_ids[s] += s * per
+        keep.append(ix)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    out_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    merge_shards_device(0, all_ids.data_ptr(), all_d.data_ptr(), S, nq, k, out_i.data_ptr(), out_d.data_ptr())
+    truth = exact_topk(X, Q, k)
+    assert recall(out_i.cpu().numpy(), truth, k) > 0.999
+    assert torch.all(out_d[:, 1:] >= out_d[:, :-1])
+    for ix in keep:
+        ix.close()

@@ -1,0 +1,506 @@
+// K1 — exact (brute-force) distance + top-k.  SURVEY.md §8a rows A9 / A10 (+ the tail of A11) and the
+// all-pairs tiles of the graph build (B1).
+//
+// Reference behaviour restated (engine/db/execution/vec_search_executor.cpp):
+//   BruteForceSearch (:717-768): distance for EVERY row of [start,end), drop deleted / filter-failing rows
+//   (the filter sees the distance), sort ascending by (distance,id).
+//   PreFilterBruteForceSearch (:770-831): deleted / filter (distance 0) first, distance for passing rows.
+// A full sort is not needed: the caller only ever reads the first min(n, limit, L_local) entries, so we
+// keep an exact top-k with the same (distance,id) order.
+//
+// Two distance kernels, both fp32 SIMT (this is exact-arithmetic work; the L2 form is the direct
+// sum of squared differences like the reference, not the |x|^2-2xy+|y|^2 expansion):
+//   * bf_dist_rows_kernel  — small batches (nq <= 16): one warp per row, coalesced float4 row loads, the
+//     query tile in shared memory, warp-shuffle reduction.  HBM-bound: N*d*4 bytes per <=8 queries.
+//   * bf_dist_tile_kernel  — large batches: 128x128x16 shared-memory tiles, 8x8 register micro-tiles.
+//     FP32-pipe bound (2*N*d*B FMA-class ops, 3 for L2).
+// followed by bf_select_kernel: threshold-filtered streaming top-k per (query, row-split).
+#include "internal.h"
+
+namespace eps {
+
+// ------------------------------------------------------------------------------------------------
+// pass bitmap: bit i set <=> row (row_start+i) is not deleted and passes the distance-free filter.
+// ------------------------------------------------------------------------------------------------
+__global__ void pass_bitmap_kernel(const uint8_t* __restrict__ deleted, int64_t deleted_bytes,
+                                   const FilterProg* __restrict__ prog, const char* __restrict__ attrs,
+                                   int64_t stride, int64_t row_start, int64_t n, uint32_t* __restrict__ pass) {
+  int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  int64_t nwords = (n + 31) >> 5;
+  if (w >= nwords) return;
+  uint32_t bits = 0;
+  for (int b = 0; b < 32; ++b) {
+    int64_t i = w * 32 + b;
+    if (i >= n) break;
+    int64_t r = row_start + i;
+    bool ok = true;
+    if (deleted && (r >> 3) < deleted_bytes) ok = !((deleted[r >> 3] >> (r & 7)) & 1);
+    if (ok && prog) ok = filter_eval(*prog, attrs, stride, r, 0.f);
+    if (ok) bits |= (1u << b);
+  }
+  pass[w] = bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small-batch distances: warp per row.
+// D[q * ldd + (r - row_start)] for q in [0,nq_tile), r in [row_start, row_start + n).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowsQT = 8;
+
+template <bool L2, bool VEC4>
+__global__ void __launch_bounds__(256) bf_dist_rows_kernel(const float* __restrict__ vectors, int dim, int metric,
+                                                           int64_t row_start, int64_t n,
+                                                           const float* __restrict__ queries, int nq_tile,
+                                                           float* __restrict__ D, int64_t ldd) {
+  extern __shared__ __align__(16) float q_smem[];  // [nq_tile][dim]
+  for (int i = threadIdx.x; i < nq_tile * dim; i += blockDim.x) q_smem[i] = queries[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (gridDim.x * static_cast<int64_t>(blockDim.x)) >> 5;
+  const int64_t ngroups = (n + 31) >> 5;
+  for (int64_t g = warp; g < ngroups; g += nwarps) {
+    float keep[kRowsQT];
+#pragma unroll
+    for (int q = 0; q < kRowsQT; ++q) keep[q] = 0.f;
+    const int64_t base = g << 5;
+    const int rows_here = static_cast<int>(min(static_cast<int64_t>(32), n - base));
+    for (int j = 0; j < rows_here; ++j) {
+      const float* row = vectors + (row_start + base + j) * static_cast<int64_t>(dim);
+      float acc[kRowsQT];
+#pragma unroll
+      for (int q = 0; q < kRowsQT; ++q) acc[q] = 0.f;
+      if (VEC4) {
+        const int dim4 = dim >> 2;
+        for (int c = lane; c < dim4; c += 32) {
+          float4 x = ldg_f4_stream(row + 4 * c);
+#pragma unroll
+          for (int q = 0; q < kRowsQT; ++q) {
+            if (q < nq_tile) {
+              float4 y = *reinterpret_cast<const float4*>(q_smem + q * dim + 4 * c);
+              if (L2) {
+                float d;
+                d = x.x - y.x; acc[q] = fmaf(d, d, acc[q]);
+                d = x.y - y.y; acc[q] = fmaf(d, d, acc[q]);
+                d = x.z - y.z; acc[q] = fmaf(d, d, acc[q]);
+                d = x.w - y.w; acc[q] = fmaf(d, d, acc[q]);
+              } else {
+                acc[q] = fmaf(x.x, y.x, acc[q]); acc[q] = fmaf(x.y, y.y, acc[q]);
+                acc[q] = fmaf(x.z, y.z, acc[q]); acc[q] = fmaf(x.w, y.w, acc[q]);
+              }
+            }
+          }
+        }
+      } else {
+        for (int i = lane; i < dim; i += 32) {
+          float x = __ldg(row + i);
+#pragma unroll
+          for (int q = 0; q < kRowsQT; ++q) {
+            if (q < nq_tile) {
+              float y = q_smem[q * dim + i];
+              if (L2) { float d = x - y; acc[q] = fmaf(d, d, acc[q]); } else { acc[q] = fmaf(x, y, acc[q]); }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kRowsQT; ++q) {
+        if (q < nq_tile) {
+          float s = warp_sum(acc[q]);
+          if (lane == j) keep[q] = s;
+        }
+      }
+    }
+    if (lane < rows_here) {
+#pragma unroll
+      for (int q = 0; q < kRowsQT; ++q)
+        if (q < nq_tile) D[q * ldd + base + lane] = finish_metric(metric, keep[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large-batch distances: 128 (rows) x 128 (queries) x 16 tiles, 256 threads, 8x8 per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBM = 128, kBN = 128, kBK = 16, kPad = 4;
+
+template <bool VEC4>
+__device__ __forceinline__ float4 load_k4(const float* __restrict__ base, int64_t row, int64_t n_rows, int dim, int k) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < n_rows) {
+    const float* p = base + row * static_cast<int64_t>(dim) + k;
+    if (VEC4) {
+      if (k < dim) v = ldg_f4(p);  // dim % 4 == 0 => k+3 < dim
+    } else {
+      if (k < dim) v.x = __ldg(p);
+      if (k + 1 < dim) v.y = __ldg(p + 1);
+      if (k + 2 < dim) v.z = __ldg(p + 2);
+      if (k + 3 < dim) v.w = __ldg(p + 3);
+    }
+  }
+  return v;
+}
+
+template <bool L2, bool VEC4>
+__global__ void __launch_bounds__(256) bf_dist_tile_kernel(const float* __restrict__ A, int64_t a_rows,
+                                                           const float* __restrict__ B, int64_t b_rows, int dim,
+                                                           int metric, float* __restrict__ D, int64_t ldd) {
+  __shared__ __align__(16) float As[2][kBK][kBM + kPad];
+  __shared__ __align__(16) float Bs[2][kBK][kBN + kPad];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t a0 = static_cast<int64_t>(blockIdx.x) * kBM;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.y) * kBN;
+  const int lrow = tid >> 2;       // 0..63
+  const int lk = (tid & 3) * 4;    // 0,4,8,12
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rb[2];
+  const int nk = (dim + kBK - 1) / kBK;
+  // prologue
+  ra[0] = load_k4<VEC4>(A, a0 + lrow, a_rows, dim, lk);
+  ra[1] = load_k4<VEC4>(A, a0 + lrow + 64, a_rows, dim, lk);
+  rb[0] = load_k4<VEC4>(B, b0 + lrow, b_rows, dim, lk);
+  rb[1] = load_k4<VEC4>(B, b0 + lrow + 64, b_rows, dim, lk);
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int r = lrow + 64 * h;
+      As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y; As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
+      Bs[buf][lk + 0][r] = rb[h].x; Bs[buf][lk + 1][r] = rb[h].y; Bs[buf][lk + 2][r] = rb[h].z; Bs[buf][lk + 3][r] = rb[h].w;
+    }
+  };
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      const int k = (kt + 1) * kBK + lk;
+      ra[0] = load_k4<VEC4>(A, a0 + lrow, a_rows, dim, k);
+      ra[1] = load_k4<VEC4>(A, a0 + lrow + 64, a_rows, dim, k);
+      rb[0] = load_k4<VEC4>(B, b0 + lrow, b_rows, dim, k);
+      rb[1] = load_k4<VEC4>(B, b0 + lrow + 64, b_rows, dim, k);
+    }
+#pragma unroll
+    for (int k = 0; k < kBK; ++k) {
+      float a[8], b[8];
+      *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8]);
+      *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8 + 4]);
+      *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 8]);
+      *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 8 + 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (L2) { float d = a[i] - b[j]; acc[i][j] = fmaf(d, d, acc[i][j]); }
+          else { acc[i][j] = fmaf(a[i], b[j], acc[i][j]); }
+        }
+    }
+    if (kt + 1 < nk) {
+      stash(cur ^ 1);
+      __syncthreads();
+    }
+  }
+  // epilogue: D[query][row]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int64_t q = b0 + tx * 8 + j;
+    if (q >= b_rows) continue;
+    const int64_t r = a0 + ty * 8;
+    float* dst = D + q * ldd + r;
+    if (r + 7 < a_rows && ((ldd & 3) == 0)) {
+      float4 v0 = make_float4(finish_metric(metric, acc[0][j]), finish_metric(metric, acc[1][j]),
+                              finish_metric(metric, acc[2][j]), finish_metric(metric, acc[3][j]));
+      float4 v1 = make_float4(finish_metric(metric, acc[4][j]), finish_metric(metric, acc[5][j]),
+                              finish_metric(metric, acc[6][j]), finish_metric(metric, acc[7][j]));
+      *reinterpret_cast<float4*>(dst) = v0;
+      *reinterpret_cast<float4*>(dst + 4) = v1;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (r + i < a_rows) dst[i] = finish_metric(metric, acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming top-k select.  One CTA per (query, split).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 256;
+constexpr int kSelItems = 4;
+constexpr int kSelRound = kSelThreads * kSelItems;  // 1024
+constexpr int kSelBuf = 2 * kSelRound;              // 2048
+
+__device__ __forceinline__ int lower_bound_keys(const unsigned long long* a, int n, unsigned long long key) {
+  int lo = 0, hi = n;
+  key &= kKeyMask;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((a[mid] & kKeyMask) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Merge the nbuf unsorted keys of buf into the sorted top-k list; result (first k) back in topk.
+__device__ void select_flush(unsigned long long* topk, unsigned long long* merged, unsigned long long* buf, int nbuf,
+                             int k) {
+  const int np = next_pow2(nbuf < 1 ? 1 : nbuf);
+  for (int i = nbuf + threadIdx.x; i < np; i += blockDim.x) buf[i] = kKeyInf;
+  __syncthreads();
+  block_bitonic_sort(buf, np);
+  for (int i = threadIdx.x; i < nbuf; i += blockDim.x) {
+    unsigned long long key = buf[i];
+    int dest = lower_bound_keys(topk, k, key) + i;
+    if (dest < k) merged[dest] = key;
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    unsigned long long key = topk[j];
+    int dest = j + lower_bound_keys(buf, nbuf, key);
+    if (dest < k) merged[dest] = key;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x) topk[j] = merged[j];
+  __syncthreads();
+}
+
+struct SelectArgs {
+  const float* D;            // [nq x ldd] distances of this chunk (KEYS_IN = false)
+  const unsigned long long* keys_in;  // [nq x n_in] candidate keys (KEYS_IN = true)
+  int64_t ldd;
+  int64_t n;                 // elements per query in this chunk
+  int64_t row_base;          // global row id of element 0
+  int nsplit;
+  int k;
+  unsigned long long* state; // [nq x nsplit x k]
+  const uint32_t* pass;      // bitmap relative to pass_base (may be null)
+  int64_t pass_base;
+  const FilterProg* dyn;     // per-candidate filter that needs the real distance (may be null)
+  const char* attrs;
+  int64_t attr_stride;
+  int64_t self_base;         // query q is row self_base + q and is excluded (-1: off)
+};
+
+template <bool KEYS_IN>
+__global__ void __launch_bounds__(kSelThreads) bf_select_kernel(SelectArgs a) {
+  extern __shared__ __align__(16) unsigned long long sel_smem[];
+  unsigned long long* topk = sel_smem;
+  unsigned long long* merged = topk + a.k;
+  unsigned long long* buf = merged + a.k;
+  __shared__ int nbuf;
+  const int q = blockIdx.x;
+  const int split = blockIdx.y;
+  unsigned long long* st = a.state + (static_cast<int64_t>(q) * a.nsplit + split) * a.k;
+  for (int j = threadIdx.x; j < a.k; j += blockDim.x) topk[j] = st[j];
+  if (threadIdx.x == 0) nbuf = 0;
+  __syncthreads();
+  unsigned long long thr = topk[a.k - 1] & kKeyMask;
+  const int64_t per = (a.n + a.nsplit - 1) / a.nsplit;
+  const int64_t begin = split * per;
+  const int64_t end = min(a.n, begin + per);
+  for (int64_t base = begin; base < end; base += kSelRound) {
+#pragma unroll
+    for (int it = 0; it < kSelItems; ++it) {
+      int64_t i = base + it * kSelThreads + threadIdx.x;
+      if (i < end) {
+        unsigned long long key;
+        int64_t row;
+        if (KEYS_IN) {
+          key = a.keys_in[static_cast<int64_t>(q) * a.n + i] & kKeyMask;
+          row = key_id(key);
+        } else {
+          row = a.row_base + i;
+          key = make_key(a.D[static_cast<int64_t>(q) * a.ldd + i], static_cast<uint32_t>(row));
+        }
+        if (key < thr && key != kKeyInf) {
+          bool ok = true;
+          if (!KEYS_IN) {
+            if (a.pass) {
+              int64_t pi = row - a.pass_base;
+              ok = (a.pass[pi >> 5] >> (pi & 31)) & 1u;
+            }
+            if (ok && a.self_base >= 0 && row == a.self_base + q) ok = false;
+            if (ok && a.dyn) ok = filter_eval(*a.dyn, a.attrs, a.attr_stride, row, key_dist(key));
+          }
+          if (ok) {
+            int slot = atomicAdd(&nbuf, 1);
+            buf[slot] = key;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (nbuf > kSelBuf - kSelRound) {
+      int n = nbuf;
+      __syncthreads();
+      select_flush(topk, merged, buf, n, a.k);
+      if (threadIdx.x == 0) nbuf = 0;
+      thr = topk[a.k - 1] & kKeyMask;
+      __syncthreads();
+    }
+  }
+  {
+    int n = nbuf;
+    __syncthreads();
+    if (n > 0) select_flush(topk, merged, buf, n, a.k);
+  }
+  for (int j = threadIdx.x; j < a.k; j += blockDim.x) st[j] = topk[j];
+}
+
+__global__ void fill_keys_kernel(unsigned long long* p, int64_t n, unsigned long long v) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host driver
+// ------------------------------------------------------------------------------------------------
+static int launch_dist(Index* ix, const float* A_base, int64_t row_start, int64_t n, const float* d_queries,
+                       int64_t nq, float* D, int64_t ldd, uint64_t* launches) {
+  const int dim = static_cast<int>(ix->dim);
+  const bool l2 = ix->metric == EPS_METRIC_L2;
+  if (nq <= 16) {
+    int qt_cap = static_cast<int>(std::min<int64_t>(kRowsQT, (200 * 1024) / (ix->dim * 4)));
+    if (qt_cap < 1) return fail(EPS_ERR_UNSUPPORTED, "dimension too large for the brute-force row kernel");
+    for (int64_t q0 = 0; q0 < nq; q0 += qt_cap) {
+      int nt = static_cast<int>(std::min<int64_t>(qt_cap, nq - q0));
+      size_t smem = static_cast<size_t>(nt) * dim * 4;
+      int64_t groups = (n + 31) / 32;
+      int blocks = static_cast<int>(std::min<int64_t>((groups + 7) / 8, static_cast<int64_t>(ix->num_sms) * 8));
+      if (blocks < 1) blocks = 1;
+#define LAUNCH_ROWS(L2_, V4_)                                                                                   \
+  do {                                                                                                          \
+    if (smem > 48 * 1024)                                                                                       \
+      EPS_CUDA(cudaFuncSetAttribute(bf_dist_rows_kernel<L2_, V4_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    static_cast<int>(smem)));                                                   \
+    bf_dist_rows_kernel<L2_, V4_><<<blocks, 256, smem, ix->stream>>>(A_base, dim, ix->metric, row_start, n,     \
+                                                                     d_queries + q0 * dim, nt, D + q0 * ldd, ldd); \
+  } while (0)
+      if (l2) { if (ix->vec4) LAUNCH_ROWS(true, true); else LAUNCH_ROWS(true, false); }
+      else { if (ix->vec4) LAUNCH_ROWS(false, true); else LAUNCH_ROWS(false, false); }
+#undef LAUNCH_ROWS
+      ++*launches;
+    }
+  } else {
+    dim3 grid(static_cast<unsigned>((n + kBM - 1) / kBM), static_cast<unsigned>((nq + kBN - 1) / kBN));
+    const float* A = A_base + row_start * ix->dim;
+    if (l2) {
+      if (ix->vec4) bf_dist_tile_kernel<true, true><<<grid, 256, 0, ix->stream>>>(A, n, d_queries, nq, dim, ix->metric, D, ldd);
+      else bf_dist_tile_kernel<true, false><<<grid, 256, 0, ix->stream>>>(A, n, d_queries, nq, dim, ix->metric, D, ldd);
+    } else {
+      if (ix->vec4) bf_dist_tile_kernel<false, true><<<grid, 256, 0, ix->stream>>>(A, n, d_queries, nq, dim, ix->metric, D, ldd);
+      else bf_dist_tile_kernel<false, false><<<grid, 256, 0, ix->stream>>>(A, n, d_queries, nq, dim, ix->metric, D, ldd);
+    }
+    ++*launches;
+  }
+  EPS_CUDA(cudaGetLastError());
+  return EPS_OK;
+}
+
+static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_start, int64_t row_end, int64_t k,
+                     const FilterProg* d_prog, const FilterProg* h_prog, bool prefilter, int64_t self_base,
+                     unsigned long long* d_topk, eps_stats* stats) {
+  if (k < 1 || k > 8192) return fail(EPS_ERR_UNSUPPORTED, "brute-force top-k supports 1 <= k <= 8192");
+  uint64_t launches = 0;
+  const int64_t n = row_end - row_start;
+  {
+    int64_t tot = nq * k;
+    fill_keys_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(d_topk, tot, kKeyInf);
+    ++launches;
+  }
+  if (n <= 0 || nq <= 0) {
+    if (stats) stats->kernel_launches += launches;
+    return EPS_OK;
+  }
+  // static pass bitmap (deleted + distance-free filter); a filter whose root compares "@distance"
+  // (and we are not in prefilter mode, where the reference feeds it distance 0) is evaluated per
+  // candidate inside the select kernel instead.
+  const bool has_prog = h_prog && h_prog->n > 0;
+  const bool dynamic = has_prog && !prefilter && h_prog->root_uses_dist;
+  const bool need_pass = ix->any_deleted || (has_prog && !dynamic);
+  uint32_t* d_pass = nullptr;
+  if (need_pass) {
+    int64_t words = (n + 31) / 32;
+    EPS_TRY(ix->s_pass.reserve(static_cast<size_t>(words) * 4));
+    d_pass = ix->s_pass.as<uint32_t>();
+    pass_bitmap_kernel<<<static_cast<unsigned>((words + 127) / 128), 128, 0, ix->stream>>>(
+        ix->any_deleted ? ix->d_deleted : nullptr, ix->deleted_bytes, (has_prog && !dynamic) ? d_prog : nullptr,
+        ix->d_attrs, ix->attr_stride, row_start, n, d_pass);
+    ++launches;
+  }
+  // chunking: distance scratch <= ~1 GiB
+  const int64_t scratch_floats = 256ll * 1024 * 1024;
+  int64_t chunk = scratch_floats / nq;
+  chunk = std::max<int64_t>(kBM, (chunk / kBM) * kBM);
+  if (chunk > n) chunk = ((n + 3) / 4) * 4;
+  EPS_TRY(ix->s_dist.reserve(static_cast<size_t>(nq) * chunk * 4));
+  float* D = ix->s_dist.as<float>();
+  // splits: enough CTAs to fill the machine, each >= 4096 elements
+  int nsplit = 1;
+  {
+    int64_t want = (2ll * ix->num_sms + nq - 1) / nq;
+    int64_t maxs = std::max<int64_t>(1, chunk / 4096);
+    nsplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, maxs), 64)));
+  }
+  unsigned long long* state = d_topk;
+  if (nsplit > 1) {
+    EPS_TRY(ix->s_topk2.reserve(static_cast<size_t>(nq) * nsplit * k * 8));
+    state = ix->s_topk2.as<unsigned long long>();
+    int64_t tot = nq * nsplit * k;
+    fill_keys_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(state, tot, kKeyInf);
+    ++launches;
+  }
+  const size_t sel_smem = (2 * static_cast<size_t>(k) + kSelBuf) * 8;
+  if (sel_smem > 48 * 1024) {
+    EPS_CUDA(cudaFuncSetAttribute(bf_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
+    EPS_CUDA(cudaFuncSetAttribute(bf_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
+  }
+  for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+    const int64_t cn = std::min(chunk, n - c0);
+    EPS_TRY(launch_dist(ix, ix->d_vectors, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
+    SelectArgs a;
+    a.D = D; a.keys_in = nullptr; a.ldd = chunk; a.n = cn; a.row_base = row_start + c0; a.nsplit = nsplit;
+    a.k = static_cast<int>(k); a.state = state; a.pass = d_pass; a.pass_base = row_start;
+    a.dyn = dynamic ? d_prog : nullptr; a.attrs = ix->d_attrs; a.attr_stride = ix->attr_stride;
+    a.self_base = self_base;
+    bf_select_kernel<false><<<dim3(static_cast<unsigned>(nq), nsplit), kSelThreads, sel_smem, ix->stream>>>(a);
+    ++launches;
+    EPS_CUDA(cudaGetLastError());
+  }
+  if (nsplit > 1) {
+    SelectArgs a;
+    a.D = nullptr; a.keys_in = state; a.ldd = 0; a.n = static_cast<int64_t>(nsplit) * k; a.row_base = 0; a.nsplit = 1;
+    a.k = static_cast<int>(k); a.state = d_topk; a.pass = nullptr; a.pass_base = 0; a.dyn = nullptr;
+    a.attrs = nullptr; a.attr_stride = 0; a.self_base = -1;
+    bf_select_kernel<true><<<dim3(static_cast<unsigned>(nq), 1), kSelThreads, sel_smem, ix->stream>>>(a);
+    ++launches;
+    EPS_CUDA(cudaGetLastError());
+  }
+  if (stats) {
+    stats->n_dist += static_cast<uint64_t>(nq) * static_cast<uint64_t>(n);
+    stats->kernel_launches += launches;
+  }
+  return EPS_OK;
+}
+
+int brute_force_topk(Index* ix, const float* d_queries, int64_t nq, int64_t row_start, int64_t row_end, int64_t k,
+                     const FilterProg* d_prog, const FilterProg* h_prog, bool prefilter, unsigned long long* d_topk,
+                     eps_stats* stats) {
+  return topk_impl(ix, d_queries, nq, row_start, row_end, k, d_prog, h_prog, prefilter, -1, d_topk, stats);
+}
+
+int brute_force_knn_rows(Index* ix, int64_t q_start, int64_t nq, int64_t n_rows, int64_t k,
+                         unsigned long long* d_topk, eps_stats* stats) {
+  bool saved = ix->any_deleted;
+  ix->any_deleted = false;  // the build indexes every row, deleted or not (ann_graph_segment.cpp:201)
+  int rc = topk_impl(ix, ix->d_vectors + q_start * ix->dim, nq, 0, n_rows, k, nullptr, nullptr, false, q_start, d_topk,
+                     stats);
+  ix->any_deleted = saved;
+  return rc;
+}
+
+}  // namespace eps

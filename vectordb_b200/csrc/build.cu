@@ -1,0 +1,418 @@
+// K4 — graph build on device.  SURVEY.md §8a rows B1-B3.
+//
+// Reference pipeline (ANNGraphSegment::BuildFromVectorTable, engine/db/ann_graph_segment.cpp:201-242):
+//   B1  kNN graph by NN-descent with the field metric (db/index/knn/nndescent.hpp, K = 100);
+//   B2  NSG refinement, always with L2 (ann_graph_segment.cpp:216-218):
+//         navigation point = vertex nearest the centroid (nsg.cpp:101-155),
+//         per vertex: candidate pool sorted by distance, MRNG-style selection — keep p unless a kept r
+//         has d(r,p) < d(v,p) — at most out_degree edges (SyncPrune :540-580, SelectEdge :655-685),
+//         reverse-edge insertion with re-selection on overflow (InterInsert :583-653),
+//         connectivity repair from the navigation point (CheckConnectivity :687-775);
+//   B3  flatten to the int64 CSR.
+// The reference build is not reproducible (rand(), racy OpenMP), so parity for the build is graph QUALITY
+// (recall / distance evaluations of searches on it), not edge identity.
+//
+// Device mapping:
+//   * kNN lists: exact all-pairs tiles (brute_force.cu) when n <= exact_knn_below, NN-descent local joins
+//     as batched gathered tiles otherwise (nn_descent.cu);
+//   * selection: the pairwise distances among a vertex's <=127 candidates are one 128x128xd gathered
+//     distance tile per vertex (pair_tile_kernel, fp32, direct (x-y)^2 form); the sequential MRNG scan then
+//     runs one warp per vertex over that matrix (select_edges_kernel);
+//   * reverse edges: atomic append into per-vertex slots, then the same tile + selection on the union;
+//   * connectivity repair + CSR flatten: integer graph work, on the host over the copied-back lists.
+#include <algorithm>
+#include <cstring>
+#include <queue>
+
+#include "internal.h"
+
+namespace eps {
+
+int nn_descent(Index* ix, int64_t n, int K, const eps_build_params& bp, unsigned long long* d_knn, eps_stats* st);
+
+constexpr int kC = 128;  // candidate slots per vertex (slot 0 = the vertex itself)
+
+// cand [batch x kC] row ids (-1 = empty).  D [batch x kC x kC] = L2^2 between candidate rows.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) pair_tile_kernel(const float* __restrict__ vectors, int dim,
+                                                        const int32_t* __restrict__ cand, float* __restrict__ D) {
+  constexpr int BK = 16, PAD = 4;
+  __shared__ __align__(16) float As[2][BK][kC + PAD];
+  __shared__ int ids[kC];
+  const int tid = threadIdx.x;
+  const int64_t z = blockIdx.x;
+  if (tid < kC) ids[tid] = cand[z * kC + tid];
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  auto load = [&](int r, int k) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int id = ids[r];
+    if (id >= 0) {
+      const float* p = vectors + static_cast<int64_t>(id) * dim + k;
+      if (VEC4) { if (k < dim) v = ldg_f4(p); }
+      else {
+        if (k < dim) v.x = __ldg(p);
+        if (k + 1 < dim) v.y = __ldg(p + 1);
+        if (k + 2 < dim) v.z = __ldg(p + 2);
+        if (k + 3 < dim) v.w = __ldg(p + 3);
+      }
+    }
+    return v;
+  };
+  float4 r0 = load(lrow, lk), r1 = load(lrow + 64, lk);
+  auto stash = [&](int buf) {
+    As[buf][lk + 0][lrow] = r0.x; As[buf][lk + 1][lrow] = r0.y; As[buf][lk + 2][lrow] = r0.z; As[buf][lk + 3][lrow] = r0.w;
+    As[buf][lk + 0][lrow + 64] = r1.x; As[buf][lk + 1][lrow + 64] = r1.y; As[buf][lk + 2][lrow + 64] = r1.z; As[buf][lk + 3][lrow + 64] = r1.w;
+  };
+  stash(0);
+  __syncthreads();
+  const int nk = (dim + BK - 1) / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) { r0 = load(lrow, (kt + 1) * BK + lk); r1 = load(lrow + 64, (kt + 1) * BK + lk); }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[8], b[8];
+      *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8]);
+      *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8 + 4]);
+      *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&As[cur][k][tx * 8]);
+      *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&As[cur][k][tx * 8 + 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { float d = a[i] - b[j]; acc[i][j] = fmaf(d, d, acc[i][j]); }
+    }
+    if (kt + 1 < nk) { stash(cur ^ 1); __syncthreads(); }
+  }
+  float* out = D + z * kC * kC;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float* dst = out + (ty * 8 + i) * kC + tx * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+}
+
+// One warp per vertex.  cand[z][0] = the vertex, cand[z][1..] = its candidates (unsorted, -1 empty).
+// Sorts candidates by (d(v,p), id), then SelectEdge: keep p unless some kept r has d(r,p) < d(v,p).
+// keep_all: skip the selection when the candidate count already fits (InterInsert's append branch).
+__global__ void select_edges_kernel(const int32_t* __restrict__ cand, const float* __restrict__ D, int batch,
+                                    int out_degree, int pool_cap, int keep_all_if_fits, int64_t v_base,
+                                    int32_t* __restrict__ out_ids, float* __restrict__ out_dist,
+                                    int32_t* __restrict__ out_cnt, int out_stride) {
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t z = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_in_block;
+  extern __shared__ __align__(16) unsigned char se_smem[];
+  // per warp: order[kC] (slot indices sorted), kept[out_degree]
+  int* order = reinterpret_cast<int*>(se_smem) + warp_in_block * (kC + 64);
+  int* kept = order + kC;
+  if (z >= batch) return;
+  const int32_t* c = cand + z * kC;
+  const float* M = D + z * kC * kC;
+  // rank candidates 1..kC-1 by (distance to v, id); empty slots last
+  int n_valid = 0;
+  for (int s = 1 + lane; s < kC; s += 32) n_valid += (c[s] >= 0);
+  n_valid = static_cast<int>(warp_sum(static_cast<float>(n_valid)));
+  for (int s = 1 + lane; s < kC; s += 32) {
+    const int id = c[s];
+    if (id < 0) continue;
+    const float d = M[s];  // row 0 = distances from v
+    int r = 0;
+    for (int t = 1; t < kC; ++t) {
+      const int id2 = c[t];
+      if (id2 < 0 || t == s) continue;
+      const float d2 = M[t];
+      r += (d2 < d) || (d2 == d && id2 < id);
+    }
+    order[r] = s;
+  }
+  __syncwarp();
+  int64_t v = v_base + z;
+  int32_t* oi = out_ids + v * out_stride;
+  float* od = out_dist + v * out_stride;
+  int nk = 0;
+  if (keep_all_if_fits && n_valid <= out_degree) {
+    for (int i = lane; i < n_valid; i += 32) { const int s = order[i]; oi[i] = c[s]; od[i] = M[s]; }
+    nk = n_valid;
+  } else {
+    const int scan = min(n_valid, pool_cap);
+    for (int i = 0; i < scan && nk < out_degree; ++i) {
+      const int s = order[i];
+      const float dvp = M[s];
+      bool viol = false;
+      for (int t = lane; t < nk; t += 32) viol |= (M[kept[t] * kC + s] < dvp);
+      if (!__any_sync(kFull, viol)) {
+        if (lane == 0) { kept[nk] = s; oi[nk] = c[s]; od[nk] = dvp; }
+        ++nk;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) out_cnt[v] = nk;
+}
+
+// cand row for pass 1: [v, knn ids...]
+__global__ void fill_cand_from_knn_kernel(const unsigned long long* __restrict__ knn, int K, int64_t v0, int batch,
+                                          int32_t* __restrict__ cand) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(batch) * kC) return;
+  const int64_t z = i / kC;
+  const int s = static_cast<int>(i % kC);
+  int32_t id = -1;
+  if (s == 0) id = static_cast<int32_t>(v0 + z);
+  else if (s - 1 < K) {
+    const unsigned long long key = knn[(v0 + z) * K + (s - 1)];
+    if ((key & kKeyMask) != kKeyInf) id = static_cast<int32_t>(key_id(key));
+  }
+  cand[i] = id;
+}
+
+// reverse candidates: for edge v -> p append v to rev[p] (first rev_cap arrivals)
+__global__ void append_reverse_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ cnt, int stride,
+                                      int64_t n, int rev_cap, int32_t* __restrict__ rev, int32_t* __restrict__ rev_cnt) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t v = i / stride;
+  const int j = static_cast<int>(i % stride);
+  if (v >= n || j >= cnt[v]) return;
+  const int p = ids[v * stride + j];
+  const int slot = atomicAdd(&rev_cnt[p], 1);
+  if (slot < rev_cap) rev[static_cast<int64_t>(p) * rev_cap + slot] = static_cast<int32_t>(v);
+}
+
+// cand row for pass 2: [v, own list..., reverse candidates not already present...]
+__global__ void fill_cand_union_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ cnt, int stride,
+                                       const int32_t* __restrict__ rev, const int32_t* __restrict__ rev_cnt, int rev_cap,
+                                       int64_t v0, int batch, int32_t* __restrict__ cand) {
+  const int64_t z = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (z >= batch) return;
+  const int64_t v = v0 + z;
+  int32_t* c = cand + z * kC;
+  int m = 0;
+  c[m++] = static_cast<int32_t>(v);
+  const int own = cnt[v];
+  for (int j = 0; j < own && m < kC; ++j) c[m++] = ids[v * stride + j];
+  const int nr = min(rev_cnt[v], rev_cap);
+  for (int j = 0; j < nr && m < kC; ++j) {
+    const int32_t u = rev[v * rev_cap + j];
+    bool dup = (u == v);
+    for (int t = 1; t <= own && !dup; ++t) dup = (c[t] == u);
+    if (!dup) c[m++] = u;
+  }
+  for (; m < kC; ++m) c[m] = -1;
+}
+
+__global__ void column_sum_kernel(const float* __restrict__ vectors, int64_t n, int dim, float* __restrict__ out) {
+  // grid.x covers columns, grid.y splits rows; atomics combine (fp32 sums like nsg.cpp:110-117)
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= dim) return;
+  const int64_t per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = blockIdx.y * per, r1 = min(n, r0 + per);
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += vectors[r * dim + col];
+  atomicAdd(&out[col], s);
+}
+__global__ void scale_kernel(float* v, int n, float s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= s;
+}
+
+static int prune_pass(Index* ix, int64_t n, const unsigned long long* d_knn, int K, bool pass2, int out_degree,
+                      int pool_cap, int32_t* d_ids, float* d_dist, int32_t* d_cnt, int stride, const int32_t* d_rev,
+                      const int32_t* d_rev_cnt, int rev_cap, int32_t* d_ids_out, float* d_dist_out, int32_t* d_cnt_out,
+                      eps_stats* st) {
+  const int64_t batch_max = 4096;
+  DevBuf cand, D;
+  EPS_TRY(cand.reserve(static_cast<size_t>(batch_max) * kC * 4));
+  EPS_TRY(D.reserve(static_cast<size_t>(batch_max) * kC * kC * 4));
+  const int warps = 4;
+  const size_t smem = static_cast<size_t>(warps) * (kC + 64) * 4;
+  for (int64_t v0 = 0; v0 < n; v0 += batch_max) {
+    const int batch = static_cast<int>(std::min(batch_max, n - v0));
+    if (!pass2) {
+      const int64_t tot = static_cast<int64_t>(batch) * kC;
+      fill_cand_from_knn_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(d_knn, K, v0, batch,
+                                                                                                cand.as<int32_t>());
+    } else {
+      fill_cand_union_kernel<<<(batch + 127) / 128, 128, 0, ix->stream>>>(d_ids, d_cnt, stride, d_rev, d_rev_cnt, rev_cap,
+                                                                          v0, batch, cand.as<int32_t>());
+    }
+    if (ix->vec4) pair_tile_kernel<true><<<batch, 256, 0, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), cand.as<int32_t>(), D.as<float>());
+    else pair_tile_kernel<false><<<batch, 256, 0, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), cand.as<int32_t>(), D.as<float>());
+    select_edges_kernel<<<(batch + warps - 1) / warps, warps * 32, smem, ix->stream>>>(
+        cand.as<int32_t>(), D.as<float>(), batch, out_degree, pool_cap, pass2 ? 1 : 0, v0, d_ids_out, d_dist_out,
+        d_cnt_out, stride);
+    EPS_CUDA(cudaGetLastError());
+    if (st) st->kernel_launches += 3;
+  }
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  cand.release();
+  D.release();
+  return EPS_OK;
+}
+
+int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
+  eps_build_params bp;
+  std::memset(&bp, 0, sizeof(bp));
+  if (params) bp = *params;
+  if (bp.knn_k <= 0) bp.knn_k = 100;          // Default_NSG_Config.knng
+  if (bp.out_degree <= 0) bp.out_degree = 50;  // .out_degree
+  if (bp.candidate_pool <= 0) bp.candidate_pool = 300;
+  if (bp.search_length <= 0) bp.search_length = 45;
+  if (bp.nnd_iters <= 0) bp.nnd_iters = 30;
+  if (bp.nnd_sample <= 0) bp.nnd_sample = 24;
+  if (bp.nnd_delta <= 0.f) bp.nnd_delta = 0.001f;
+  if (bp.exact_knn_below <= 0) bp.exact_knn_below = 60000;
+  if (n < 2 || n > ix->n_rows) return fail(EPS_ERR_INVALID_ARGUMENT, "build: n out of range");
+  if (n >= (1ll << 31)) return fail(EPS_ERR_UNSUPPORTED, "build: more than 2^31 rows per shard");
+  const int R = std::min<int>(bp.out_degree, 64);
+  const int K = static_cast<int>(std::min<int64_t>(std::min<int>(bp.knn_k, kC - 1), n - 1));
+  eps_stats st;
+  std::memset(&st, 0, sizeof(st));
+
+  // ---- B1: kNN lists (field metric) -------------------------------------------------------
+  DevBuf knn;
+  EPS_TRY(knn.reserve(static_cast<size_t>(n) * K * 8));
+  if (n <= bp.exact_knn_below) {
+    const int64_t qc = 8192;
+    for (int64_t q0 = 0; q0 < n; q0 += qc) {
+      const int64_t nq = std::min(qc, n - q0);
+      EPS_TRY(brute_force_knn_rows(ix, q0, nq, n, K, knn.as<unsigned long long>() + q0 * K, &st));
+    }
+  } else {
+    EPS_TRY(nn_descent(ix, n, K, bp, knn.as<unsigned long long>(), &st));
+  }
+
+  // ---- B2a: navigation point = exact nearest row to the centroid (L2) ----------------------
+  int64_t nav = 0;
+  {
+    DevBuf cen, top;
+    EPS_TRY(cen.reserve(static_cast<size_t>(ix->dim) * 4));
+    EPS_TRY(top.reserve(8));
+    EPS_CUDA(cudaMemsetAsync(cen.p, 0, static_cast<size_t>(ix->dim) * 4, ix->stream));
+    dim3 g(static_cast<unsigned>((ix->dim + 127) / 128), static_cast<unsigned>(std::min<int64_t>(1024, (n + 255) / 256)));
+    column_sum_kernel<<<g, 128, 0, ix->stream>>>(ix->d_vectors, n, static_cast<int>(ix->dim), cen.as<float>());
+    scale_kernel<<<static_cast<unsigned>((ix->dim + 127) / 128), 128, 0, ix->stream>>>(cen.as<float>(), static_cast<int>(ix->dim), 1.0f / static_cast<float>(n));
+    const int saved_metric = ix->metric;
+    const bool saved_del = ix->any_deleted;
+    ix->metric = EPS_METRIC_L2;
+    ix->any_deleted = false;
+    int rc = brute_force_topk(ix, cen.as<float>(), 1, 0, n, 1, nullptr, nullptr, false, top.as<unsigned long long>(), &st);
+    ix->metric = saved_metric;
+    ix->any_deleted = saved_del;
+    EPS_TRY(rc);
+    unsigned long long key;
+    EPS_CUDA(cudaMemcpyAsync(&key, top.p, 8, cudaMemcpyDeviceToHost, ix->stream));
+    EPS_CUDA(cudaStreamSynchronize(ix->stream));
+    nav = key_id(key);
+    cen.release();
+    top.release();
+  }
+
+  // ---- B2b: selection pass 1 (SyncPrune / SelectEdge) --------------------------------------
+  const int stride = 64;  // >= R
+  DevBuf ids1, dist1, cnt1, ids2, dist2, cnt2, rev, rev_cnt;
+  EPS_TRY(ids1.reserve(static_cast<size_t>(n) * stride * 4));
+  EPS_TRY(dist1.reserve(static_cast<size_t>(n) * stride * 4));
+  EPS_TRY(cnt1.reserve(static_cast<size_t>(n) * 4));
+  EPS_TRY(prune_pass(ix, n, knn.as<unsigned long long>(), K, false, R, bp.candidate_pool, nullptr, nullptr, nullptr, stride,
+                     nullptr, nullptr, 0, ids1.as<int32_t>(), dist1.as<float>(), cnt1.as<int32_t>(), &st));
+
+  // ---- B2c: reverse edges (InterInsert) ----------------------------------------------------
+  const int rev_cap = kC - 1 - R;  // union always fits the candidate slots
+  EPS_TRY(rev.reserve(static_cast<size_t>(n) * rev_cap * 4));
+  EPS_TRY(rev_cnt.reserve(static_cast<size_t>(n) * 4));
+  EPS_CUDA(cudaMemsetAsync(rev_cnt.p, 0, static_cast<size_t>(n) * 4, ix->stream));
+  {
+    const int64_t tot = n * stride;
+    append_reverse_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(
+        ids1.as<int32_t>(), cnt1.as<int32_t>(), stride, n, rev_cap, rev.as<int32_t>(), rev_cnt.as<int32_t>());
+    EPS_CUDA(cudaGetLastError());
+  }
+  EPS_TRY(ids2.reserve(static_cast<size_t>(n) * stride * 4));
+  EPS_TRY(dist2.reserve(static_cast<size_t>(n) * stride * 4));
+  EPS_TRY(cnt2.reserve(static_cast<size_t>(n) * 4));
+  EPS_TRY(prune_pass(ix, n, nullptr, 0, true, R, kC, ids1.as<int32_t>(), dist1.as<float>(), cnt1.as<int32_t>(), stride,
+                     rev.as<int32_t>(), rev_cnt.as<int32_t>(), rev_cap, ids2.as<int32_t>(), dist2.as<float>(),
+                     cnt2.as<int32_t>(), &st));
+
+  // ---- B2d + B3: connectivity repair and CSR flatten (host, integer work) -------------------
+  std::vector<int32_t> h_ids(static_cast<size_t>(n) * stride), h_cnt(static_cast<size_t>(n));
+  EPS_CUDA(cudaMemcpyAsync(h_ids.data(), ids2.p, h_ids.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+  EPS_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt2.p, h_cnt.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+  std::vector<unsigned long long> h_knn(static_cast<size_t>(n) * K);
+  EPS_CUDA(cudaMemcpyAsync(h_knn.data(), knn.p, h_knn.size() * 8, cudaMemcpyDeviceToHost, ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  ids1.release(); dist1.release(); cnt1.release(); ids2.release(); dist2.release(); cnt2.release();
+  rev.release(); rev_cnt.release(); knn.release();
+
+  std::vector<std::vector<int32_t>> extra(static_cast<size_t>(n));  // edges added by the repair
+  {
+    std::vector<uint8_t> seen(static_cast<size_t>(n), 0);
+    std::vector<int32_t> stack;
+    int64_t linked = 0;
+    auto flood = [&](int32_t root) {
+      if (seen[root]) return;
+      seen[root] = 1; ++linked;
+      stack.push_back(root);
+      while (!stack.empty()) {
+        const int32_t u = stack.back();
+        stack.pop_back();
+        const int32_t* row = &h_ids[static_cast<size_t>(u) * stride];
+        for (int j = 0; j < h_cnt[u]; ++j) {
+          const int32_t w = row[j];
+          if (!seen[w]) { seen[w] = 1; ++linked; stack.push_back(w); }
+        }
+        for (int32_t w : extra[u]) if (!seen[w]) { seen[w] = 1; ++linked; stack.push_back(w); }
+      }
+    };
+    flood(static_cast<int32_t>(nav));
+    int64_t scan = 0;
+    while (linked < n) {
+      while (scan < n && seen[scan]) ++scan;  // FindUnconnectedNode: first unlinked id (:736-742)
+      if (scan >= n) break;
+      const int32_t u = static_cast<int32_t>(scan);
+      // nearest already-linked vertex among u's kNN list (the reference searches for it, :751-766)
+      int32_t root = static_cast<int32_t>(nav);
+      for (int j = 0; j < K; ++j) {
+        const unsigned long long key = h_knn[static_cast<size_t>(u) * K + j];
+        if ((key & kKeyMask) == kKeyInf) break;
+        const int32_t w = static_cast<int32_t>(key_id(key));
+        if (seen[w]) { root = w; break; }
+      }
+      extra[root].push_back(u);  // nsg[root].push_back(id) (:774), may exceed out_degree (Q11)
+      flood(u);
+    }
+  }
+  std::vector<int64_t> off(static_cast<size_t>(n) + 1);
+  int64_t e = 0;
+  for (int64_t v = 0; v < n; ++v) { off[v] = e; e += h_cnt[v] + static_cast<int64_t>(extra[v].size()); }
+  off[n] = e;
+  std::vector<int32_t> nb(static_cast<size_t>(e));
+  for (int64_t v = 0; v < n; ++v) {
+    int64_t o = off[v];
+    for (int j = 0; j < h_cnt[v]; ++j) nb[o++] = h_ids[static_cast<size_t>(v) * stride + j];
+    for (int32_t w : extra[v]) nb[o++] = w;
+  }
+  // install
+  if (ix->d_offsets) { cudaFree(ix->d_offsets); ix->d_offsets = nullptr; }
+  if (ix->d_nbrs) { cudaFree(ix->d_nbrs); ix->d_nbrs = nullptr; }
+  if (ix->d_init_ids) { cudaFree(ix->d_init_ids); ix->d_init_ids = nullptr; }
+  ix->init_L = 0;
+  EPS_CUDA(cudaMalloc(&ix->d_offsets, (static_cast<size_t>(n) + 1) * 8));
+  EPS_CUDA(cudaMalloc(&ix->d_nbrs, std::max<size_t>(static_cast<size_t>(e), 1) * 4));
+  EPS_CUDA(cudaMemcpyAsync(ix->d_offsets, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+  if (e > 0) EPS_CUDA(cudaMemcpyAsync(ix->d_nbrs, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->n_indexed = n;
+  ix->n_edges = e;
+  ix->nav = nav;
+  return EPS_OK;
+}
+
+}  // namespace eps

@@ -1,0 +1,490 @@
+// C ABI of libepsilla_b200 (include/epsilla_b200.h): index lifetime, segment mirrors, and the batched
+// VecSearchExecutor::Search orchestration (engine/db/execution/vec_search_executor.cpp:833-935).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "internal.h"
+
+namespace eps {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap && p) return EPS_OK;
+  if (p) { cudaFree(p); p = nullptr; cap = 0; }
+  size_t want = bytes < 256 ? 256 : bytes;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    return fail(EPS_ERR_OOM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+  }
+  cap = want;
+  return EPS_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+static int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(EPS_ERR_NO_DEVICE, std::string("no usable CUDA device (libepsilla_b200 has no CPU path): ") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+  if (device < 0 || device >= n) return fail(EPS_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+  EPS_CUDA(cudaSetDevice(device));
+  return EPS_OK;
+}
+
+// Validate and lower the caller's node array (see filter.cuh).
+int lower_filter(const eps_filter_node* nodes, int64_t n, FilterProg* out) {
+  std::memset(out, 0, sizeof(*out));
+  if (n <= 0 || nodes == nullptr) return EPS_OK;
+  if (n > kMaxFilterNodes) return fail(EPS_ERR_UNSUPPORTED, "filter has more than 48 nodes");
+  for (int64_t i = 0; i < n; ++i) {
+    const eps_filter_node& s = nodes[i];
+    FNode& d = out->nodes[i];
+    const int t = static_cast<int>(s.node_type);
+    switch (t) {
+      case NT_IntConst: d.value = static_cast<double>(s.int_value); break;
+      case NT_DoubleConst: d.value = s.double_value; break;
+      case NT_BoolConst: d.value = s.bool_value ? 1.0 : 0.0; break;
+      case NT_Int1Attr: case NT_Int2Attr: case NT_Int4Attr: case NT_Int8Attr: case NT_BoolAttr:
+        if (s.field_offset < 0) return fail(EPS_ERR_INVALID_ARGUMENT, "filter attribute node without a field offset");
+        break;
+      case NT_DoubleAttr: case NT_FloatAttr:
+        if (s.field_offset < 0 && s.field_offset != -2)
+          return fail(EPS_ERR_INVALID_ARGUMENT, "filter attribute node without a field offset");
+        if (s.field_offset == -2) out->uses_distance = 1;
+        break;
+      case NT_Add: case NT_Subtract: case NT_Multiply: case NT_Divide: case NT_Module: case NT_LT: case NT_LTE:
+      case NT_EQ: case NT_GT: case NT_GTE: case NT_NE: case NT_AND: case NT_OR:
+        if (s.left < 0 || s.left >= i || s.right < 0 || s.right >= i)
+          return fail(EPS_ERR_INVALID_ARGUMENT, "filter node children must precede the node");
+        break;
+      case NT_NOT:
+        if (s.left < 0 || s.left >= i) return fail(EPS_ERR_INVALID_ARGUMENT, "filter NOT child must precede the node");
+        break;
+      default:
+        return fail(EPS_ERR_UNSUPPORTED,
+                    "filter node type " + std::to_string(t) + " (string / IN / LIKE / geo / aggregation) is out of scope");
+    }
+    d.type = static_cast<int16_t>(t);
+    d.vtype = static_cast<int16_t>(s.value_type);
+    d.left = static_cast<int16_t>(s.left < 0 ? 0 : s.left);
+    d.right = static_cast<int16_t>(s.right < 0 ? 0 : s.right);
+    d.field_offset = static_cast<int32_t>(s.field_offset);
+  }
+  out->n = static_cast<int>(n);
+  const FNode& r = out->nodes[n - 1];
+  const bool cmp = r.type == NT_GT || r.type == NT_GTE || r.type == NT_LT || r.type == NT_LTE;
+  const bool eq = (r.type == NT_EQ || r.type == NT_NE) && out->nodes[r.left].vtype != VT_BOOL &&
+                  out->nodes[r.left].vtype != VT_STRING;
+  out->root_uses_dist = (out->uses_distance && (cmp || eq)) ? 1 : 0;
+  return EPS_OK;
+}
+
+__global__ void pair_distance_kernel(int metric, int vec4, const float* __restrict__ a, const float* __restrict__ b,
+                                     int64_t n, int dim, float* __restrict__ out) {
+  const int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  float d = warp_distance(metric, vec4 != 0, a + w * dim, b + w * dim, dim, lane);
+  if (lane == 0) out[w] = d;
+}
+
+// engine::Normalize (db/vector.cpp:60-69): v /= sqrt(sum v^2), fp32.
+__global__ void normalize_kernel(float* __restrict__ v, int64_t n, int dim) {
+  const int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  float* p = v + w * dim;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s = fmaf(p[i], p[i], s);
+  s = sqrtf(warp_sum(s));
+  for (int i = lane; i < dim; i += 32) p[i] = p[i] / s;
+}
+
+int normalize_rows_device(cudaStream_t s, float* d, int64_t n, int64_t dim) {
+  normalize_kernel<<<static_cast<unsigned>((n * 32 + 127) / 128), 128, 0, s>>>(d, n, static_cast<int>(dim));
+  EPS_CUDA(cudaGetLastError());
+  return EPS_OK;
+}
+
+static void free_graph(Index* ix) {
+  if (ix->d_offsets) cudaFree(ix->d_offsets);
+  if (ix->d_nbrs) cudaFree(ix->d_nbrs);
+  if (ix->d_init_ids) cudaFree(ix->d_init_ids);
+  ix->d_offsets = nullptr;
+  ix->d_nbrs = nullptr;
+  ix->d_init_ids = nullptr;
+  ix->init_L = 0;
+  ix->n_indexed = 0;
+  ix->n_edges = 0;
+}
+
+static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t limit, const eps_filter_node* filter,
+                         int64_t n_filter, int64_t* d_ids, float* d_dists, int64_t* d_counts, eps_stats* stats) {
+  if (nq <= 0) return EPS_OK;
+  if (limit < 1) return fail(EPS_ERR_INVALID_ARGUMENT, "limit must be >= 1");
+  FilterProg h_prog;
+  EPS_TRY(lower_filter(filter, n_filter, &h_prog));
+  const FilterProg* d_prog = nullptr;
+  if (h_prog.n > 0) {
+    if (!ix->d_attrs) {
+      bool needs_attrs = false;
+      for (int i = 0; i < h_prog.n; ++i) needs_attrs |= h_prog.nodes[i].field_offset >= 0;
+      if (needs_attrs) return fail(EPS_ERR_INVALID_ARGUMENT, "filter reads attributes but eps_index_set_attrs was not called");
+    }
+    EPS_TRY(ix->s_filter.reserve(sizeof(FilterProg)));
+    EPS_CUDA(cudaMemcpyAsync(ix->s_filter.p, &h_prog, sizeof(FilterProg), cudaMemcpyHostToDevice, ix->stream));
+    // h_prog lives on this stack frame until the sync at the end of the caller's timing region; the copy
+    // from pageable memory is staged synchronously by the runtime, so it is safe.
+    d_prog = ix->s_filter.as<FilterProg>();
+  }
+  const int64_t total = ix->n_rows;
+  const int64_t n_indexed = ix->n_indexed;
+  const bool brute = ix->prefilter || ix->force_brute || n_indexed < 512;  // BruteforceThreshold (hpp:28)
+  eps_stats local;
+  std::memset(&local, 0, sizeof(local));
+  EPS_CUDA(cudaEventRecord(ix->ev[1], ix->stream));
+  if (brute) {
+    if (limit > 8192) return fail(EPS_ERR_UNSUPPORTED, "limit above 8192 is not supported");
+    const int64_t k = limit;
+    EPS_TRY(ix->s_topk.reserve(static_cast<size_t>(nq) * k * 8));
+    EPS_TRY(brute_force_topk(ix, d_queries, nq, 0, total, k, d_prog, &h_prog, ix->prefilter,
+                             ix->s_topk.as<unsigned long long>(), &local));
+    EPS_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
+    // :857 prefilter: min(size, limit); :864 brute: min(size, limit, L_local)
+    const int64_t cap = (ix->prefilter || ix->force_brute) ? limit : std::min<int64_t>(limit, ix->L_local);
+    EPS_TRY(finalize_keys(ix, ix->s_topk.as<unsigned long long>(), nq, k, limit, cap, d_ids, d_dists, d_counts));
+    local.kernel_launches += 1;
+  } else {
+    const int64_t L = std::min<int64_t>(ix->L_master, n_indexed);  // Q1 clamp
+    const int64_t search_limit = std::min<int64_t>(std::min<int64_t>(n_indexed, limit), ix->L_local);  // :872
+    EPS_TRY(ix->s_queue.reserve(static_cast<size_t>(nq) * L * 8));
+    EPS_TRY(graph_search(ix, d_queries, nq, L, ix->s_queue.as<unsigned long long>(), &local));
+    ix->graph_counters_pending = true;
+    EPS_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
+    const unsigned long long* d_tail = nullptr;
+    int64_t tail_k = 0;
+    if (total > n_indexed) {  // :885-900
+      tail_k = std::min<int64_t>(std::min<int64_t>(limit, total - n_indexed), 8192);
+      EPS_TRY(ix->s_tail.reserve(static_cast<size_t>(nq) * tail_k * 8));
+      EPS_TRY(brute_force_topk(ix, d_queries, nq, n_indexed, total, tail_k, d_prog, &h_prog, false,
+                               ix->s_tail.as<unsigned long long>(), &local));
+      d_tail = ix->s_tail.as<unsigned long long>();
+    }
+    EPS_TRY(finalize_graph(ix, ix->s_queue.as<unsigned long long>(), nq, L, search_limit, L, d_tail, tail_k, limit,
+                           d_prog, &h_prog, d_ids, d_dists, d_counts));
+    local.kernel_launches += 1;
+  }
+  if (stats) {
+    stats->n_dist += local.n_dist;
+    stats->n_seed += local.n_seed;
+    stats->n_expand += local.n_expand;
+    stats->n_edges += local.n_edges;
+    stats->n_queries += static_cast<uint64_t>(nq);
+    stats->kernel_launches += local.kernel_launches;
+  }
+  return EPS_OK;
+}
+
+}  // namespace eps
+
+using eps::Index;
+
+extern "C" {
+
+const char* eps_last_error(void) { return eps::g_err.c_str(); }
+const char* eps_version(void) { return "epsilla_b200 0.1 (sm_100a)"; }
+int eps_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int eps_index_create(eps_index** out, int metric, int64_t dim, const float* host_vectors, int64_t capacity_rows,
+                     int device) {
+  if (!out) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  if (dim < 1 || capacity_rows < 0) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "bad dim / capacity");
+  if (metric != EPS_METRIC_L2 && metric != EPS_METRIC_COSINE && metric != EPS_METRIC_IP)
+    metric = EPS_METRIC_L2;  // GetDistFunc default branch (db/index/index.cpp:19-20)
+  EPS_TRY(eps::check_device(device));
+  Index* ix = new Index();
+  ix->device = device;
+  ix->metric = metric;
+  ix->dim = dim;
+  ix->capacity = capacity_rows;
+  ix->host_vectors = host_vectors;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->num_sms = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete ix; return eps::fail(EPS_ERR_CUDA, cudaGetErrorString(e)); }
+  for (auto& ev : ix->ev) cudaEventCreate(&ev);
+  if (capacity_rows > 0 && host_vectors) {
+    e = cudaMalloc(&ix->d_vectors, static_cast<size_t>(capacity_rows) * dim * 4);
+    if (e != cudaSuccess) {
+      cudaStreamDestroy(ix->stream);
+      delete ix;
+      return eps::fail(EPS_ERR_OOM, std::string("vector table: ") + cudaGetErrorString(e));
+    }
+    ix->owns_vectors = true;
+  }
+  ix->vec4 = (dim % 4 == 0);
+  *out = reinterpret_cast<eps_index*>(ix);
+  return EPS_OK;
+}
+
+void eps_index_destroy(eps_index* h) {
+  if (!h) return;
+  Index* ix = reinterpret_cast<Index*>(h);
+  cudaSetDevice(ix->device);
+  cudaStreamSynchronize(ix->stream);
+  eps::free_graph(ix);
+  if (ix->owns_vectors && ix->d_vectors) cudaFree(ix->d_vectors);
+  if (ix->d_deleted) cudaFree(ix->d_deleted);
+  if (ix->d_attrs) cudaFree(ix->d_attrs);
+  eps::DevBuf* bufs[] = {&ix->s_queries, &ix->s_dist, &ix->s_topk, &ix->s_topk2, &ix->s_pass, &ix->s_filter,
+                         &ix->s_visited, &ix->s_queue, &ix->s_tail, &ix->s_out_ids, &ix->s_out_dists,
+                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc};
+  for (auto* b : bufs) b->release();
+  for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(ix->stream);
+  delete ix;
+}
+
+int eps_index_sync_rows(eps_index* h, int64_t n_rows_now) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  EPS_TRY(eps::check_device(ix->device));
+  if (!ix->owns_vectors) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "index has no host vector table to mirror");
+  if (n_rows_now < ix->n_rows || n_rows_now > ix->capacity)
+    return eps::fail(EPS_ERR_INVALID_ARGUMENT, "n_rows_now outside [mirrored rows, capacity]");
+  if (n_rows_now > ix->n_rows) {
+    const size_t off = static_cast<size_t>(ix->n_rows) * ix->dim;
+    const size_t cnt = static_cast<size_t>(n_rows_now - ix->n_rows) * ix->dim;
+    EPS_CUDA(cudaMemcpyAsync(ix->d_vectors + off, ix->host_vectors + off, cnt * 4, cudaMemcpyHostToDevice, ix->stream));
+    EPS_CUDA(cudaStreamSynchronize(ix->stream));
+    ix->n_rows = n_rows_now;
+  }
+  return EPS_OK;
+}
+
+int eps_index_adopt_device_rows(eps_index* h, const float* d_vectors, int64_t n_rows) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix || !d_vectors) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument");
+  EPS_TRY(eps::check_device(ix->device));
+  if (ix->owns_vectors && ix->d_vectors) cudaFree(ix->d_vectors);
+  ix->owns_vectors = false;
+  ix->d_vectors = const_cast<float*>(d_vectors);
+  ix->n_rows = n_rows;
+  if (n_rows > ix->capacity) ix->capacity = n_rows;
+  ix->vec4 = (ix->dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_vectors) & 15) == 0);
+  return EPS_OK;
+}
+
+int eps_index_set_graph(eps_index* h, int64_t n_indexed, const int64_t* offsets, const int64_t* nbrs, int64_t nav) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  EPS_TRY(eps::check_device(ix->device));
+  eps::free_graph(ix);
+  if (n_indexed <= 0) return EPS_OK;
+  if (!offsets) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null offset table");
+  if (n_indexed > ix->n_rows) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "graph covers rows that are not mirrored yet");
+  if (n_indexed >= (1ll << 31)) return eps::fail(EPS_ERR_UNSUPPORTED, "more than 2^31 indexed rows");
+  if (nav < 0 || nav >= n_indexed) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "navigation point out of range");
+  const int64_t e = offsets[n_indexed];
+  std::vector<int32_t> nb32(static_cast<size_t>(e > 0 ? e : 1));
+  for (int64_t i = 0; i < e; ++i) {
+    if (nbrs[i] < 0 || nbrs[i] >= n_indexed) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "neighbor id out of range");
+    nb32[i] = static_cast<int32_t>(nbrs[i]);
+  }
+  EPS_CUDA(cudaMalloc(&ix->d_offsets, (static_cast<size_t>(n_indexed) + 1) * 8));
+  EPS_CUDA(cudaMalloc(&ix->d_nbrs, nb32.size() * 4));
+  EPS_CUDA(cudaMemcpyAsync(ix->d_offsets, offsets, (static_cast<size_t>(n_indexed) + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
+  EPS_CUDA(cudaMemcpyAsync(ix->d_nbrs, nb32.data(), nb32.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->n_indexed = n_indexed;
+  ix->n_edges = e;
+  ix->nav = nav;
+  return EPS_OK;
+}
+
+int eps_index_build(eps_index* h, int64_t n, const eps_build_params* params) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  EPS_TRY(eps::check_device(ix->device));
+  return eps::build_graph(ix, n, params);
+}
+
+int eps_index_get_graph(eps_index* h, int64_t* n_indexed, int64_t* n_edges, int64_t* offsets, int64_t* nbrs,
+                        int64_t* nav) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  EPS_TRY(eps::check_device(ix->device));
+  if (n_indexed) *n_indexed = ix->n_indexed;
+  if (n_edges) *n_edges = ix->n_edges;
+  if (nav) *nav = ix->nav;
+  if (ix->n_indexed == 0) return EPS_OK;
+  if (offsets) EPS_CUDA(cudaMemcpy(offsets, ix->d_offsets, (static_cast<size_t>(ix->n_indexed) + 1) * 8, cudaMemcpyDeviceToHost));
+  if (nbrs && ix->n_edges > 0) {
+    std::vector<int32_t> nb32(static_cast<size_t>(ix->n_edges));
+    EPS_CUDA(cudaMemcpy(nb32.data(), ix->d_nbrs, nb32.size() * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < ix->n_edges; ++i) nbrs[i] = nb32[i];
+  }
+  return EPS_OK;
+}
+
+int eps_index_set_deleted(eps_index* h, const uint8_t* bitset, int64_t nbytes) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  EPS_TRY(eps::check_device(ix->device));
+  if (!bitset || nbytes <= 0) { ix->any_deleted = false; return EPS_OK; }
+  if (nbytes > ix->deleted_bytes) {
+    if (ix->d_deleted) cudaFree(ix->d_deleted);
+    ix->d_deleted = nullptr;
+    EPS_CUDA(cudaMalloc(&ix->d_deleted, static_cast<size_t>(nbytes)));
+  }
+  ix->deleted_bytes = nbytes;
+  EPS_CUDA(cudaMemcpyAsync(ix->d_deleted, bitset, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice, ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  bool any = false;
+  for (int64_t i = 0; i < nbytes && !any; ++i) any = bitset[i] != 0;
+  ix->any_deleted = any;
+  return EPS_OK;
+}
+
+int eps_index_set_attrs(eps_index* h, const char* table, int64_t stride, int64_t n_rows) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  EPS_TRY(eps::check_device(ix->device));
+  if (ix->d_attrs) { cudaFree(ix->d_attrs); ix->d_attrs = nullptr; }
+  ix->attr_stride = stride;
+  ix->attr_rows = n_rows;
+  if (!table || stride <= 0 || n_rows <= 0) return EPS_OK;
+  EPS_CUDA(cudaMalloc(&ix->d_attrs, static_cast<size_t>(stride) * n_rows));
+  EPS_CUDA(cudaMemcpyAsync(ix->d_attrs, table, static_cast<size_t>(stride) * n_rows, cudaMemcpyHostToDevice, ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  return EPS_OK;
+}
+
+int eps_index_config(eps_index* h, int64_t L_master, int64_t L_local, int prefilter, int force_brute) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  if (L_master < 1 || L_local < 1) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "queue sizes must be >= 1");
+  ix->L_master = L_master;
+  ix->L_local = L_local;
+  ix->prefilter = prefilter != 0;
+  ix->force_brute = force_brute != 0;
+  return EPS_OK;
+}
+
+int eps_search_batch_device(eps_index* h, const float* d_queries, int64_t nq, int64_t limit,
+                            const eps_filter_node* filter, int64_t n_filter, int64_t* d_out_ids, float* d_out_dists,
+                            int64_t* d_out_counts, eps_stats* stats, int sync) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix || !d_queries || !d_out_ids || !d_out_dists || !d_out_counts)
+    return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument");
+  EPS_TRY(eps::check_device(ix->device));
+  EPS_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
+  EPS_TRY(eps::search_device(ix, d_queries, nq, limit, filter, n_filter, d_out_ids, d_out_dists, d_out_counts, stats));
+  EPS_CUDA(cudaEventRecord(ix->ev[3], ix->stream));
+  if (sync || stats) {
+    EPS_CUDA(cudaStreamSynchronize(ix->stream));
+    if (stats) {
+      if (ix->graph_counters_pending) { EPS_TRY(eps::read_graph_counters(ix, stats)); ix->graph_counters_pending = false; }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]);
+      stats->kernel_ms += ms;
+      cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]);
+      stats->total_ms += ms;
+    }
+  }
+  return EPS_OK;
+}
+
+int eps_search_batch(eps_index* h, const float* queries, int64_t nq, int64_t limit, const eps_filter_node* filter,
+                     int64_t n_filter, int64_t* out_ids, double* out_dists, int64_t* out_counts, eps_stats* stats) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix || !queries || !out_ids || !out_dists || !out_counts) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument");
+  if (nq <= 0) return EPS_OK;
+  EPS_TRY(eps::check_device(ix->device));
+  EPS_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
+  EPS_TRY(ix->s_queries.reserve(static_cast<size_t>(nq) * ix->dim * 4));
+  EPS_TRY(ix->s_out_ids.reserve(static_cast<size_t>(nq) * limit * 8));
+  EPS_TRY(ix->s_out_dists.reserve(static_cast<size_t>(nq) * limit * 4));
+  EPS_TRY(ix->s_out_counts.reserve(static_cast<size_t>(nq) * 8));
+  EPS_CUDA(cudaMemcpyAsync(ix->s_queries.p, queries, static_cast<size_t>(nq) * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
+  EPS_TRY(eps::search_device(ix, ix->s_queries.as<float>(), nq, limit, filter, n_filter, ix->s_out_ids.as<int64_t>(),
+                             ix->s_out_dists.as<float>(), ix->s_out_counts.as<int64_t>(), stats));
+  std::vector<float> hd(static_cast<size_t>(nq) * limit);
+  EPS_CUDA(cudaMemcpyAsync(out_ids, ix->s_out_ids.p, static_cast<size_t>(nq) * limit * 8, cudaMemcpyDeviceToHost, ix->stream));
+  EPS_CUDA(cudaMemcpyAsync(hd.data(), ix->s_out_dists.p, hd.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+  EPS_CUDA(cudaMemcpyAsync(out_counts, ix->s_out_counts.p, static_cast<size_t>(nq) * 8, cudaMemcpyDeviceToHost, ix->stream));
+  EPS_CUDA(cudaEventRecord(ix->ev[3], ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  for (size_t i = 0; i < hd.size(); ++i) out_dists[i] = static_cast<double>(hd[i]);  // distance_ is vector<double> (hpp:52)
+  if (stats) {
+    if (ix->graph_counters_pending) { EPS_TRY(eps::read_graph_counters(ix, stats)); ix->graph_counters_pending = false; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]);
+    stats->kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]);
+    stats->total_ms += ms;
+  }
+  return EPS_OK;
+}
+
+int eps_merge_shards_device(int device, const int64_t* d_ids, const float* d_dists, int64_t n_shards, int64_t nq,
+                            int64_t k, int64_t* d_out_ids, float* d_out_dists) {
+  EPS_TRY(eps::check_device(device));
+  EPS_TRY(eps::merge_shards(device, nullptr, d_ids, d_dists, n_shards, nq, k, d_out_ids, d_out_dists));
+  EPS_CUDA(cudaStreamSynchronize(nullptr));
+  return EPS_OK;
+}
+
+int eps_normalize(int device, float* host_vectors, int64_t nq, int64_t dim) {
+  EPS_TRY(eps::check_device(device));
+  if (nq <= 0) return EPS_OK;
+  float* d = nullptr;
+  EPS_CUDA(cudaMalloc(&d, static_cast<size_t>(nq) * dim * 4));
+  cudaMemcpy(d, host_vectors, static_cast<size_t>(nq) * dim * 4, cudaMemcpyHostToDevice);
+  int rc = eps::normalize_rows_device(nullptr, d, nq, dim);
+  cudaMemcpy(host_vectors, d, static_cast<size_t>(nq) * dim * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return rc;
+}
+
+int eps_pair_distances(int device, int metric, const float* a, const float* b, int64_t n, int64_t dim, float* out) {
+  EPS_TRY(eps::check_device(device));
+  if (n <= 0) return EPS_OK;
+  float *da = nullptr, *db = nullptr, *dout = nullptr;
+  const size_t bytes = static_cast<size_t>(n) * dim * 4;
+  EPS_CUDA(cudaMalloc(&da, bytes));
+  EPS_CUDA(cudaMalloc(&db, bytes));
+  EPS_CUDA(cudaMalloc(&dout, static_cast<size_t>(n) * 4));
+  cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
+  eps::pair_distance_kernel<<<static_cast<unsigned>((n * 32 + 127) / 128), 128>>>(metric, dim % 4 == 0 ? 1 : 0, da, db, n,
+                                                                                 static_cast<int>(dim), dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(out, dout, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost);
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  if (e != cudaSuccess) return eps::fail(EPS_ERR_CUDA, cudaGetErrorString(e));
+  return EPS_OK;
+}
+
+void* eps_index_stream(eps_index* h) { return h ? reinterpret_cast<Index*>(h)->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// K2 — batched best-first graph search.  SURVEY.md §8a rows A4-A8.
+//
+// What the reference computes (engine/db/execution/vec_search_executor.cpp, IntraQueryThreads = 1, the
+// only configuration in which it is a pure function of its inputs — SURVEY.md §5/§8c):
+//   InitializeSetLPara (:446-485)  seed the queue with the L query-independent init ids, mark them
+//                                  visited, sort by (distance,id);
+//   SearchImpl (:518-715)          repeatedly expand the first unchecked queue entry;
+//   ExpandOneCandidate (:384-444)  for each CSR neighbour: skip if visited, mark, distance, reject if
+//                                  dist > worst-in-queue, else AddIntoQueue (:75-117, sorted insert with
+//                                  eviction); return the lowest insert position r;
+//   k = (r <= k) ? r : k+1 (:648-652); stop when no unchecked entry is left.
+// The queue after one expansion is the top-L by (distance,id) of {queue ∪ unvisited neighbours}, whatever
+// the insertion order, and r is the final position of the smallest inserted entry; so evaluating all
+// neighbour distances of a vertex in parallel and merging them at once is equivalent.
+//
+// Mapping: a persistent grid, one CTA per in-flight query (queries are claimed from an atomic counter),
+// the sorted queue and the query vector in shared memory, one warp per neighbour row (coalesced 128-bit
+// streaming loads, warp-shuffle reduction), a per-CTA visited bitmap in global memory (L2-resident),
+// block-parallel rank-and-shift merge instead of the reference's memmove insert.
+#include "internal.h"
+
+namespace eps {
+
+constexpr int kCH = 64;  // neighbours handled per merge round
+
+struct GSArgs {
+  const float* vectors;
+  const int64_t* offsets;
+  const int32_t* nbrs;
+  const int32_t* init_ids;
+  const float* queries;
+  uint32_t* visited;            // [slots x visited_words]
+  unsigned long long* out_queue;  // [nq x L]
+  int* work_counter;
+  unsigned long long* stats;    // n_dist, n_expand, n_edges, n_seed
+  int64_t visited_words;
+  int dim, metric, vec4;
+  int L, Lp;
+  int nq;
+};
+
+__device__ __forceinline__ int lb_masked(const unsigned long long* a, int n, unsigned long long key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((a[mid] & kKeyMask) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128, 8) graph_search_kernel(GSArgs a) {
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  unsigned long long* queue = reinterpret_cast<unsigned long long*>(gs_smem);          // [Lp]
+  unsigned long long* cand = queue + a.Lp;                                             // [kCH] accepted, unsorted
+  unsigned long long* cs = cand + kCH;                                                 // [kCH] accepted, sorted
+  float* qv = reinterpret_cast<float*>(cs + kCH);                                      // [dim padded to 4]
+  int* pos = reinterpret_cast<int*>(qv + ((a.dim + 3) & ~3));                          // [kCH]
+  int* fresh = pos + kCH;                                                              // [kCH]
+  __shared__ int s_q, s_cur, s_nfresh, s_nacc, s_pmin;
+  __shared__ unsigned long long s_ndist, s_nexp, s_nedge;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint32_t* visited = a.visited + static_cast<int64_t>(blockIdx.x) * a.visited_words;
+  const int L = a.L;
+  if (tid == 0) { s_ndist = 0; s_nexp = 0; s_nedge = 0; }
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_q = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int q = s_q;
+    if (q >= a.nq) break;
+    for (int i = tid; i < a.dim; i += blockDim.x) qv[i] = a.queries[static_cast<int64_t>(q) * a.dim + i];
+    for (int i = L + tid; i < a.Lp; i += blockDim.x) queue[i] = kKeyInf;
+    if (tid == 0) { s_nfresh = 0; s_nacc = 0; }
+    __syncthreads();
+
+    // ---- seed (InitializeSetLPara) ----
+    for (int i = tid; i < L; i += blockDim.x) {
+      uint32_t id = static_cast<uint32_t>(a.init_ids[i]);
+      atomicOr(&visited[id >> 5], 1u << (id & 31));
+    }
+    for (int i = warp; i < L; i += nwarps) {
+      const int id = a.init_ids[i];
+      float d = warp_distance(a.metric, a.vec4 != 0, a.vectors + static_cast<int64_t>(id) * a.dim, qv, a.dim, lane);
+      if (lane == 0) queue[i] = make_key(d, static_cast<uint32_t>(id));
+    }
+    __syncthreads();
+    block_bitonic_sort(queue, a.Lp);
+
+    // ---- best-first loop (SearchImpl) ----
+    int k = 0;
+    for (;;) {
+      if (warp == 0) {
+        int found = -1;
+        for (int p = k; p < L; p += 32) {
+          int idx = p + lane;
+          bool un = idx < L && !(queue[idx] & kCheckedBit);
+          unsigned b = __ballot_sync(kFull, un);
+          if (b) { found = p + __ffs(b) - 1; break; }
+        }
+        if (lane == 0) {
+          s_cur = found;
+          s_pmin = L;
+          if (found >= 0) queue[found] |= kCheckedBit;
+        }
+      }
+      __syncthreads();
+      const int cur = s_cur;
+      if (cur < 0) break;
+      const int c = static_cast<int>(key_id(queue[cur]));
+      const int64_t e0 = a.offsets[c], e1 = a.offsets[c + 1];
+      if (tid == 0) { ++s_nexp; s_nedge += static_cast<unsigned long long>(e1 - e0); }
+
+      for (int64_t eb = e0; eb < e1; eb += kCH) {
+        const int cnt = static_cast<int>(min(static_cast<int64_t>(kCH), e1 - eb));
+        // visited test-and-set (ExpandOneCandidate :403-406)
+        if (tid < cnt) {
+          const uint32_t nb = static_cast<uint32_t>(a.nbrs[eb + tid]);
+          const uint32_t bit = 1u << (nb & 31);
+          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
+          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = static_cast<int>(nb);
+        }
+        __syncthreads();
+        const int nfresh = s_nfresh;
+        const unsigned long long bound = queue[L - 1] & kKeyMask;  // live worst entry (:546)
+        for (int i = warp; i < nfresh; i += nwarps) {
+          const int nb = fresh[i];
+          float d = warp_distance(a.metric, a.vec4 != 0, a.vectors + static_cast<int64_t>(nb) * a.dim, qv, a.dim, lane);
+          if (lane == 0) {
+            unsigned long long key = make_key(d, static_cast<uint32_t>(nb));
+            if (key < bound) cand[atomicAdd(&s_nacc, 1)] = key;  // dist > bound rejected (:424); ties by id
+          }
+        }
+        __syncthreads();
+        const int m = s_nacc;
+        if (tid == 0) { s_ndist += static_cast<unsigned long long>(nfresh); s_nfresh = 0; s_nacc = 0; }
+        if (m > 0) {
+          // 1. sort the accepted candidates (rank by counting; keys are distinct)
+          for (int i = tid; i < m; i += blockDim.x) {
+            const unsigned long long key = cand[i];
+            int r = 0;
+            for (int j = 0; j < m; ++j) r += (cand[j] < key);
+            cs[r] = key;
+          }
+          __syncthreads();
+          // 2. insertion points in the current queue
+          for (int i = tid; i < m; i += blockDim.x) pos[i] = lb_masked(queue, L, cs[i]);
+          __syncthreads();
+          const int p0 = pos[0];
+          // 3. shift old entries right by the number of candidates that precede them, top tile first
+          for (int hi = L; hi > p0; hi -= blockDim.x) {
+            const int j = hi - 1 - tid;
+            unsigned long long key = 0;
+            int dest = L;
+            if (j >= p0) {
+              key = queue[j];
+              int lo = 0, up = m;  // s = #{i : pos[i] <= j}
+              while (lo < up) { int mid = (lo + up) >> 1; if (pos[mid] <= j) lo = mid + 1; else up = mid; }
+              dest = j + lo;
+            }
+            __syncthreads();
+            if (dest < L) queue[dest] = key;
+            __syncthreads();
+          }
+          // 4. drop the candidates into their holes
+          for (int i = tid; i < m; i += blockDim.x) {
+            const int f = pos[i] + i;
+            if (f < L) queue[f] = cs[i];
+          }
+          if (tid == 0 && p0 < s_pmin) s_pmin = p0;
+        }
+        __syncthreads();  // counters reset + queue settled before the next round
+      }
+      const int pmin = s_pmin;
+      k = (pmin <= k) ? pmin : k + 1;  // :648-652
+    }
+
+    // ---- results + visited reset (:711-714) ----
+    unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
+    for (int i = tid; i < L; i += blockDim.x) out[i] = queue[i];
+    {
+      uint4* v4 = reinterpret_cast<uint4*>(visited);
+      const int64_t n4 = a.visited_words >> 2;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int64_t i = tid; i < n4; i += blockDim.x) v4[i] = z;
+    }
+    if (tid == 0) s_ndist += static_cast<unsigned long long>(L);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(&a.stats[0], s_ndist);
+    atomicAdd(&a.stats[1], s_nexp);
+    atomicAdd(&a.stats[2], s_nedge);
+  }
+}
+
+// PrepareInitIds (vec_search_executor.cpp:487-516): dedup'd out-neighbours of the navigation point, then
+// ids nav+1, nav+2, ... (mod n) until L entries.  Pure index logic on <= L + deg entries; runs on the host
+// over the navigation row copied back from the device.  L is clamped to n_indexed by the caller (the
+// reference loops forever when L > n_indexed).
+int prepare_init_ids(Index* ix, int64_t L) {
+  if (ix->init_L == L && ix->d_init_ids) return EPS_OK;
+  int64_t e[2];
+  EPS_CUDA(cudaMemcpyAsync(e, ix->d_offsets + ix->nav, 16, cudaMemcpyDeviceToHost, ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  std::vector<int32_t> row(static_cast<size_t>(e[1] - e[0]));
+  if (!row.empty()) {
+    EPS_CUDA(cudaMemcpyAsync(row.data(), ix->d_nbrs + e[0], row.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+    EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  }
+  std::vector<int32_t> ids;
+  ids.reserve(static_cast<size_t>(L));
+  std::vector<bool> sel(static_cast<size_t>(ix->n_indexed), false);
+  for (size_t i = 0; i < row.size() && static_cast<int64_t>(ids.size()) < L; ++i) {
+    int32_t v = row[i];
+    if (sel[v]) continue;
+    sel[v] = true;
+    ids.push_back(v);
+  }
+  int64_t tmp = ix->nav + 1;
+  while (static_cast<int64_t>(ids.size()) < L) {
+    if (tmp == ix->n_indexed) tmp = 0;
+    int64_t v = tmp++;
+    if (sel[v]) continue;
+    sel[v] = true;
+    ids.push_back(static_cast<int32_t>(v));
+  }
+  if (ix->d_init_ids) { cudaFree(ix->d_init_ids); ix->d_init_ids = nullptr; }
+  EPS_CUDA(cudaMalloc(&ix->d_init_ids, static_cast<size_t>(L) * 4));
+  EPS_CUDA(cudaMemcpyAsync(ix->d_init_ids, ids.data(), static_cast<size_t>(L) * 4, cudaMemcpyHostToDevice, ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->init_L = L;
+  return EPS_OK;
+}
+
+int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsigned long long* d_queue,
+                 eps_stats* stats) {
+  if (L < 1 || L > ix->n_indexed) return fail(EPS_ERR_INVALID_ARGUMENT, "graph_search: L out of range");
+  const int Lp = next_pow2(static_cast<int>(L));
+  if (Lp > 16384) return fail(EPS_ERR_UNSUPPORTED, "SearchQueueSize above 16384 is not supported by the graph kernel");
+  EPS_TRY(prepare_init_ids(ix, L));
+  const int dimp = (static_cast<int>(ix->dim) + 3) & ~3;
+  const size_t smem = static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4;
+  if (smem > 220 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query do not fit in shared memory");
+  EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel, 128, smem));
+  if (per_sm < 1) per_sm = 1;
+  int slots = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(per_sm) * ix->num_sms));
+  const int64_t words = ((ix->n_indexed + 31) / 32 + 3) & ~3ll;
+  if (ix->visited_slots < slots || ix->s_visited.cap < static_cast<size_t>(slots) * words * 4) {
+    EPS_TRY(ix->s_visited.reserve(static_cast<size_t>(slots) * words * 4));
+    ix->visited_slots = slots;
+  }
+  // bitmaps must start clean; the kernel leaves them clean.  (Re)zero when the geometry changed.
+  if (ix->vis_clean_ptr != ix->s_visited.p || ix->vis_clean_words != words) {
+    EPS_CUDA(cudaMemsetAsync(ix->s_visited.p, 0, ix->s_visited.cap, ix->stream));
+    ix->vis_clean_ptr = ix->s_visited.p;
+    ix->vis_clean_words = words;
+  }
+  EPS_TRY(ix->s_misc.reserve(64));
+  EPS_CUDA(cudaMemsetAsync(ix->s_misc.p, 0, 64, ix->stream));
+  GSArgs a;
+  a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.init_ids = ix->d_init_ids;
+  a.queries = d_queries; a.visited = ix->s_visited.as<uint32_t>(); a.out_queue = d_queue;
+  a.work_counter = reinterpret_cast<int*>(ix->s_misc.as<unsigned char>() + 32);
+  a.stats = ix->s_misc.as<unsigned long long>();
+  a.visited_words = words; a.dim = static_cast<int>(ix->dim); a.metric = ix->metric; a.vec4 = ix->vec4 ? 1 : 0;
+  a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
+  graph_search_kernel<<<slots, 128, smem, ix->stream>>>(a);
+  EPS_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->n_seed += static_cast<uint64_t>(nq) * static_cast<uint64_t>(L);
+    stats->kernel_launches += 1;
+  }
+  return EPS_OK;
+}
+
+// Device counters of the last graph_search launch (call after the stream has been synchronised).
+int read_graph_counters(Index* ix, eps_stats* stats) {
+  if (!stats || !ix->s_misc.p) return EPS_OK;
+  unsigned long long h[4];
+  EPS_CUDA(cudaMemcpy(h, ix->s_misc.p, 32, cudaMemcpyDeviceToHost));
+  stats->n_dist += h[0];
+  stats->n_expand += h[1];
+  stats->n_edges += h[2];
+  return EPS_OK;
+}
+
+}  // namespace eps

@@ -1,0 +1,107 @@
+// Internal host-side declarations shared by the translation units of libepsilla_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "filter.cuh"
+
+namespace eps {
+
+// Device buffer that grows on demand (never shrinks); owned by an index / a call context.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() { return static_cast<T*>(p); }
+};
+
+struct Index {
+  int device = 0;
+  int metric = EPS_METRIC_L2;
+  int64_t dim = 0;
+  int64_t capacity = 0;
+  const float* host_vectors = nullptr;
+  float* d_vectors = nullptr;   // [capacity x dim] (owned unless adopted)
+  bool owns_vectors = false;
+  int64_t n_rows = 0;           // rows mirrored so far (record_number_ snapshot)
+  bool vec4 = false;            // dim % 4 == 0 and 16-B aligned base
+
+  // graph (ANNGraphSegment mirror)
+  int64_t n_indexed = 0;
+  int64_t n_edges = 0;
+  int64_t nav = 0;
+  int64_t* d_offsets = nullptr;  // [n_indexed + 1]
+  int32_t* d_nbrs = nullptr;     // [n_edges]
+  int32_t* d_init_ids = nullptr; // seed set for init_L
+  int64_t init_L = 0;
+
+  // segment mirrors
+  uint8_t* d_deleted = nullptr;
+  int64_t deleted_bytes = 0;
+  bool any_deleted = false;
+  char* d_attrs = nullptr;
+  int64_t attr_stride = 0;
+  int64_t attr_rows = 0;
+
+  // executor parameters
+  int64_t L_master = 500, L_local = 500;
+  bool prefilter = false;
+  bool force_brute = false;
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int num_sms = 148;
+
+  // scratch
+  DevBuf s_queries, s_dist, s_topk, s_topk2, s_pass, s_filter, s_visited, s_queue, s_tail, s_out_ids, s_out_dists,
+      s_out_counts, s_stats, s_misc;
+  int64_t visited_slots = 0;
+  const void* vis_clean_ptr = nullptr;  // geometry for which the visited bitmaps are known to be zero
+  int64_t vis_clean_words = 0;
+  bool graph_counters_pending = false;
+};
+
+// ---- brute_force.cu ------------------------------------------------------------------------
+// Exact top-k of rows [row_start,row_end) for nq device queries.  Writes per-query sorted keys
+// (make_key(dist,row)) to d_topk [nq x k] (kKeyInf padded).  Applies deleted bits and, if
+// prog != nullptr, the filter (prefilter=true evaluates it with distance 0).
+int brute_force_topk(Index* ix, const float* d_queries, int64_t nq, int64_t row_start, int64_t row_end, int64_t k,
+                     const FilterProg* d_prog, const FilterProg* h_prog, bool prefilter, unsigned long long* d_topk,
+                     eps_stats* stats);
+
+// All-pairs variant used by the graph build: for queries = rows [q_start, q_start+nq) of the table.
+int brute_force_knn_rows(Index* ix, int64_t q_start, int64_t nq, int64_t n_rows, int64_t k,
+                         unsigned long long* d_topk, eps_stats* stats);
+
+// ---- graph_search.cu -----------------------------------------------------------------------
+// Best-first search of nq queries over the installed CSR graph with queue length L (<= n_indexed).
+// Output: d_queue [nq x L] sorted keys.
+int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsigned long long* d_queue,
+                 eps_stats* stats);
+int prepare_init_ids(Index* ix, int64_t L);
+int read_graph_counters(Index* ix, eps_stats* stats);
+
+// ---- finalize.cu ---------------------------------------------------------------------------
+// Post-filter walk / tail merge of VecSearchExecutor::Search (vec_search_executor.cpp:885-927).
+int finalize_graph(Index* ix, unsigned long long* d_queue, int64_t nq, int64_t L, int64_t search_limit,
+                   int64_t cand_num, const unsigned long long* d_tail, int64_t tail_k, int64_t limit,
+                   const FilterProg* d_prog, const FilterProg* h_prog, int64_t* d_ids, float* d_dists,
+                   int64_t* d_counts);
+// Brute-force results: first min(valid, limit_cap) keys -> ids/dists/counts.
+int finalize_keys(Index* ix, const unsigned long long* d_topk, int64_t nq, int64_t k, int64_t limit, int64_t cap,
+                  int64_t* d_ids, float* d_dists, int64_t* d_counts);
+int merge_shards(int device, cudaStream_t stream, const int64_t* d_ids, const float* d_dists, int64_t n_shards,
+                 int64_t nq, int64_t k, int64_t* d_out_ids, float* d_out_dists);
+
+// ---- build.cu ------------------------------------------------------------------------------
+int build_graph(Index* ix, int64_t n, const eps_build_params* params);
+
+// ---- misc kernels (capi.cu) ----------------------------------------------------------------
+int normalize_rows_device(cudaStream_t s, float* d, int64_t n, int64_t dim);
+
+}  // namespace eps
