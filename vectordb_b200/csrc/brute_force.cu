@@ -334,9 +334,10 @@ __global__ void __launch_bounds__(kSelThreads) bf_select_kernel(SelectArgs a) {
       }
     }
     __syncthreads();
-    if (nbuf > kSelBuf - kSelRound) {
-      int n = nbuf;
-      __syncthreads();
+    const int n_now = nbuf;
+    __syncthreads();  // nobody may bump nbuf for the next round before everyone has read it
+    if (n_now > kSelBuf - kSelRound) {
+      int n = n_now;
       select_flush(topk, merged, buf, n, a.k);
       if (threadIdx.x == 0) nbuf = 0;
       thr = topk[a.k - 1] & kKeyMask;

@@ -21,6 +21,7 @@
 //   * reverse edges: atomic append into per-vertex slots, then the same tile + selection on the union;
 //   * connectivity repair + CSR flatten: integer graph work, on the host over the copied-back lists.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <queue>
 
@@ -128,7 +129,7 @@ __global__ void select_edges_kernel(const int32_t* __restrict__ cand, const floa
       const int id2 = c[t];
       if (id2 < 0 || t == s) continue;
       const float d2 = M[t];
-      r += (d2 < d) || (d2 == d && id2 < id);
+      r += (d2 < d) || (d2 == d && (id2 < id || (id2 == id && t < s)));  // total order: ranks are a permutation
     }
     order[r] = s;
   }
@@ -244,6 +245,7 @@ static int prune_pass(Index* ix, int64_t n, const unsigned long long* d_knn, int
     }
     if (ix->vec4) pair_tile_kernel<true><<<batch, 256, 0, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), cand.as<int32_t>(), D.as<float>());
     else pair_tile_kernel<false><<<batch, 256, 0, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), cand.as<int32_t>(), D.as<float>());
+    if (getenv("EPS_DEBUG_SYNC")) EPS_CUDA(cudaStreamSynchronize(ix->stream));
     select_edges_kernel<<<(batch + warps - 1) / warps, warps * 32, smem, ix->stream>>>(
         cand.as<int32_t>(), D.as<float>(), batch, out_degree, pool_cap, pass2 ? 1 : 0, v0, d_ids_out, d_dist_out,
         d_cnt_out, stride);
@@ -284,6 +286,7 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
       const int64_t nq = std::min(qc, n - q0);
       EPS_TRY(brute_force_knn_rows(ix, q0, nq, n, K, knn.as<unsigned long long>() + q0 * K, &st));
     }
+    EPS_CUDA(cudaStreamSynchronize(ix->stream));
   } else {
     EPS_TRY(nn_descent(ix, n, K, bp, knn.as<unsigned long long>(), &st));
   }

@@ -20,7 +20,7 @@ int fail(int code, const std::string& msg);
     cudaError_t _e = (expr);                                                                      \
     if (_e != cudaSuccess) {                                                                      \
       return ::eps::fail(_e == cudaErrorMemoryAllocation ? EPS_ERR_OOM : EPS_ERR_CUDA,            \
-                         std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+                         std::string(__FILE__) + ":" + std::to_string(__LINE__) + " " + #expr + ": " + cudaGetErrorString(_e));                    \
     }                                                                                             \
   } while (0)
 

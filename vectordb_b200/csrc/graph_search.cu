@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(128, 8) graph_search_kernel(GSArgs a) {
       if (cur < 0) break;
       const int c = static_cast<int>(key_id(queue[cur]));
       const int64_t e0 = a.offsets[c], e1 = a.offsets[c + 1];
+      __syncthreads();  // everyone holds cur before warp 0 may publish the next one
       if (tid == 0) { ++s_nexp; s_nedge += static_cast<unsigned long long>(e1 - e0); }
 
       for (int64_t eb = e0; eb < e1; eb += kCH) {
@@ -134,7 +135,6 @@ __global__ void __launch_bounds__(128, 8) graph_search_kernel(GSArgs a) {
         }
         __syncthreads();
         const int m = s_nacc;
-        if (tid == 0) { s_ndist += static_cast<unsigned long long>(nfresh); s_nfresh = 0; s_nacc = 0; }
         if (m > 0) {
           // 1. sort the accepted candidates (rank by counting; keys are distinct)
           for (int i = tid; i < m; i += blockDim.x) {
@@ -170,10 +170,12 @@ __global__ void __launch_bounds__(128, 8) graph_search_kernel(GSArgs a) {
           }
           if (tid == 0 && p0 < s_pmin) s_pmin = p0;
         }
+        // every thread has read m (the m > 0 path passed barriers since; m == 0 rewrites 0 with 0)
+        if (tid == 0) { s_ndist += static_cast<unsigned long long>(nfresh); s_nfresh = 0; s_nacc = 0; }
         __syncthreads();  // counters reset + queue settled before the next round
       }
       const int pmin = s_pmin;
-      k = (pmin <= k) ? pmin : k + 1;  // :648-652
+      k = (pmin <= k) ? pmin : k + 1;  // :648-652 (only warp 0 consumes k)
     }
 
     // ---- results + visited reset (:711-714) ----
