@@ -84,6 +84,8 @@ typedef struct eps_build_params {
   int32_t exact_knn_below; /* use exact all-pairs kNN when n <= this (0 = library default) */
   int32_t seed;
   float nnd_delta;         /* NN-descent stop rate (reference 0.001) */
+  int32_t min_degree;      /* degree floor: top up with nearest rejected candidates (0 = default 32) */
+  float alpha;             /* occlusion slack: keep p unless alpha*d(r,p) < d(v,p) (0 = 1.0, the reference rule) */
   int32_t reserved;
 } eps_build_params;
 

@@ -26,85 +26,18 @@
 #include <queue>
 
 #include "internal.h"
+#include "tile.cuh"
 
 namespace eps {
 
 int nn_descent(Index* ix, int64_t n, int K, const eps_build_params& bp, unsigned long long* d_knn, eps_stats* st);
 
-constexpr int kC = 128;  // candidate slots per vertex (slot 0 = the vertex itself)
-
-// cand [batch x kC] row ids (-1 = empty).  D [batch x kC x kC] = L2^2 between candidate rows.
-template <bool VEC4>
-__global__ void __launch_bounds__(256) pair_tile_kernel(const float* __restrict__ vectors, int dim,
-                                                        const int32_t* __restrict__ cand, float* __restrict__ D) {
-  constexpr int BK = 16, PAD = 4;
-  __shared__ __align__(16) float As[2][BK][kC + PAD];
-  __shared__ int ids[kC];
-  const int tid = threadIdx.x;
-  const int64_t z = blockIdx.x;
-  if (tid < kC) ids[tid] = cand[z * kC + tid];
-  __syncthreads();
-  const int tx = tid & 15, ty = tid >> 4;
-  const int lrow = tid >> 2, lk = (tid & 3) * 4;
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  auto load = [&](int r, int k) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int id = ids[r];
-    if (id >= 0) {
-      const float* p = vectors + static_cast<int64_t>(id) * dim + k;
-      if (VEC4) { if (k < dim) v = ldg_f4(p); }
-      else {
-        if (k < dim) v.x = __ldg(p);
-        if (k + 1 < dim) v.y = __ldg(p + 1);
-        if (k + 2 < dim) v.z = __ldg(p + 2);
-        if (k + 3 < dim) v.w = __ldg(p + 3);
-      }
-    }
-    return v;
-  };
-  float4 r0 = load(lrow, lk), r1 = load(lrow + 64, lk);
-  auto stash = [&](int buf) {
-    As[buf][lk + 0][lrow] = r0.x; As[buf][lk + 1][lrow] = r0.y; As[buf][lk + 2][lrow] = r0.z; As[buf][lk + 3][lrow] = r0.w;
-    As[buf][lk + 0][lrow + 64] = r1.x; As[buf][lk + 1][lrow + 64] = r1.y; As[buf][lk + 2][lrow + 64] = r1.z; As[buf][lk + 3][lrow + 64] = r1.w;
-  };
-  stash(0);
-  __syncthreads();
-  const int nk = (dim + BK - 1) / BK;
-  for (int kt = 0; kt < nk; ++kt) {
-    const int cur = kt & 1;
-    if (kt + 1 < nk) { r0 = load(lrow, (kt + 1) * BK + lk); r1 = load(lrow + 64, (kt + 1) * BK + lk); }
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float a[8], b[8];
-      *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8]);
-      *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8 + 4]);
-      *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&As[cur][k][tx * 8]);
-      *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&As[cur][k][tx * 8 + 4]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { float d = a[i] - b[j]; acc[i][j] = fmaf(d, d, acc[i][j]); }
-    }
-    if (kt + 1 < nk) { stash(cur ^ 1); __syncthreads(); }
-  }
-  float* out = D + z * kC * kC;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float* dst = out + (ty * 8 + i) * kC + tx * 8;
-    *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-  }
-}
-
 // One warp per vertex.  cand[z][0] = the vertex, cand[z][1..] = its candidates (unsorted, -1 empty).
 // Sorts candidates by (d(v,p), id), then SelectEdge: keep p unless some kept r has d(r,p) < d(v,p).
 // keep_all: skip the selection when the candidate count already fits (InterInsert's append branch).
 __global__ void select_edges_kernel(const int32_t* __restrict__ cand, const float* __restrict__ D, int batch,
-                                    int out_degree, int pool_cap, int keep_all_if_fits, int64_t v_base,
+                                    int out_degree, int pool_cap, int keep_all_if_fits, int min_degree, float alpha,
+                                    int64_t v_base,
                                     int32_t* __restrict__ out_ids, float* __restrict__ out_dist,
                                     int32_t* __restrict__ out_cnt, int out_stride) {
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,11 +80,26 @@ __global__ void select_edges_kernel(const int32_t* __restrict__ cand, const floa
       const int s = order[i];
       const float dvp = M[s];
       bool viol = false;
-      for (int t = lane; t < nk; t += 32) viol |= (M[kept[t] * kC + s] < dvp);
+      for (int t = lane; t < nk; t += 32) viol |= (alpha * M[kept[t] * kC + s] < dvp);
       if (!__any_sync(kFull, viol)) {
         if (lane == 0) { kept[nk] = s; oi[nk] = c[s]; od[nk] = dvp; }
         ++nk;
         __syncwarp();
+      }
+    }
+    // Degree floor: the reference's pool (every vertex its build-time search evaluated, up to 300 scanned)
+    // is far more spread out than a kNN list, which the occlusion rule thins to a handful of edges on
+    // concentrated data; top the list up with the nearest rejected candidates (build).
+    if (nk < min_degree) {
+      for (int i = 0; i < scan && nk < min_degree && nk < out_degree; ++i) {
+        const int s = order[i];
+        bool have = false;
+        for (int t = lane; t < nk; t += 32) have |= (kept[t] == s);
+        if (!__any_sync(kFull, have)) {
+          if (lane == 0) { kept[nk] = s; oi[nk] = c[s]; od[nk] = M[s]; }
+          ++nk;
+          __syncwarp();
+        }
       }
     }
   }
@@ -224,7 +172,7 @@ __global__ void scale_kernel(float* v, int n, float s) {
 }
 
 static int prune_pass(Index* ix, int64_t n, const unsigned long long* d_knn, int K, bool pass2, int out_degree,
-                      int pool_cap, int32_t* d_ids, float* d_dist, int32_t* d_cnt, int stride, const int32_t* d_rev,
+                      int pool_cap, int min_degree, float alpha, int32_t* d_ids, float* d_dist, int32_t* d_cnt, int stride, const int32_t* d_rev,
                       const int32_t* d_rev_cnt, int rev_cap, int32_t* d_ids_out, float* d_dist_out, int32_t* d_cnt_out,
                       eps_stats* st) {
   const int64_t batch_max = 4096;
@@ -243,12 +191,11 @@ static int prune_pass(Index* ix, int64_t n, const unsigned long long* d_knn, int
       fill_cand_union_kernel<<<(batch + 127) / 128, 128, 0, ix->stream>>>(d_ids, d_cnt, stride, d_rev, d_rev_cnt, rev_cap,
                                                                           v0, batch, cand.as<int32_t>());
     }
-    if (ix->vec4) pair_tile_kernel<true><<<batch, 256, 0, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), cand.as<int32_t>(), D.as<float>());
-    else pair_tile_kernel<false><<<batch, 256, 0, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), cand.as<int32_t>(), D.as<float>());
+    EPS_TRY(launch_pair_tiles(ix, EPS_METRIC_L2, cand.as<int32_t>(), D.as<float>(), batch));
     if (getenv("EPS_DEBUG_SYNC")) EPS_CUDA(cudaStreamSynchronize(ix->stream));
     select_edges_kernel<<<(batch + warps - 1) / warps, warps * 32, smem, ix->stream>>>(
-        cand.as<int32_t>(), D.as<float>(), batch, out_degree, pool_cap, pass2 ? 1 : 0, v0, d_ids_out, d_dist_out,
-        d_cnt_out, stride);
+        cand.as<int32_t>(), D.as<float>(), batch, out_degree, pool_cap, pass2 ? 1 : 0, min_degree, alpha, v0, d_ids_out,
+        d_dist_out, d_cnt_out, stride);
     EPS_CUDA(cudaGetLastError());
     if (st) st->kernel_launches += 3;
   }
@@ -267,12 +214,14 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
   if (bp.candidate_pool <= 0) bp.candidate_pool = 300;
   if (bp.search_length <= 0) bp.search_length = 45;
   if (bp.nnd_iters <= 0) bp.nnd_iters = 30;
-  if (bp.nnd_sample <= 0) bp.nnd_sample = 24;
+  if (bp.nnd_sample <= 0) bp.nnd_sample = 32;
   if (bp.nnd_delta <= 0.f) bp.nnd_delta = 0.001f;
   if (bp.exact_knn_below <= 0) bp.exact_knn_below = 60000;
   if (n < 2 || n > ix->n_rows) return fail(EPS_ERR_INVALID_ARGUMENT, "build: n out of range");
   if (n >= (1ll << 31)) return fail(EPS_ERR_UNSUPPORTED, "build: more than 2^31 rows per shard");
   const int R = std::min<int>(bp.out_degree, 64);
+  const int min_deg = std::min<int>(bp.min_degree > 0 ? bp.min_degree : 32, R);
+  const float alpha = bp.alpha > 0.f ? bp.alpha : 1.0f;
   const int K = static_cast<int>(std::min<int64_t>(std::min<int>(bp.knn_k, kC - 1), n - 1));
   eps_stats st;
   std::memset(&st, 0, sizeof(st));
@@ -323,7 +272,7 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
   EPS_TRY(ids1.reserve(static_cast<size_t>(n) * stride * 4));
   EPS_TRY(dist1.reserve(static_cast<size_t>(n) * stride * 4));
   EPS_TRY(cnt1.reserve(static_cast<size_t>(n) * 4));
-  EPS_TRY(prune_pass(ix, n, knn.as<unsigned long long>(), K, false, R, bp.candidate_pool, nullptr, nullptr, nullptr, stride,
+  EPS_TRY(prune_pass(ix, n, knn.as<unsigned long long>(), K, false, R, bp.candidate_pool, min_deg, alpha, nullptr, nullptr, nullptr, stride,
                      nullptr, nullptr, 0, ids1.as<int32_t>(), dist1.as<float>(), cnt1.as<int32_t>(), &st));
 
   // ---- B2c: reverse edges (InterInsert) ----------------------------------------------------
@@ -340,7 +289,7 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
   EPS_TRY(ids2.reserve(static_cast<size_t>(n) * stride * 4));
   EPS_TRY(dist2.reserve(static_cast<size_t>(n) * stride * 4));
   EPS_TRY(cnt2.reserve(static_cast<size_t>(n) * 4));
-  EPS_TRY(prune_pass(ix, n, nullptr, 0, true, R, kC, ids1.as<int32_t>(), dist1.as<float>(), cnt1.as<int32_t>(), stride,
+  EPS_TRY(prune_pass(ix, n, nullptr, 0, true, R, kC, min_deg, alpha, ids1.as<int32_t>(), dist1.as<float>(), cnt1.as<int32_t>(), stride,
                      rev.as<int32_t>(), rev_cnt.as<int32_t>(), rev_cap, ids2.as<int32_t>(), dist2.as<float>(),
                      cnt2.as<int32_t>(), &st));
 

@@ -36,7 +36,7 @@ class BuildParams(C.Structure):
     _fields_ = [("knn_k", C.c_int32), ("out_degree", C.c_int32), ("candidate_pool", C.c_int32),
                 ("search_length", C.c_int32), ("nnd_iters", C.c_int32), ("nnd_sample", C.c_int32),
                 ("exact_knn_below", C.c_int32), ("seed", C.c_int32), ("nnd_delta", C.c_float),
-                ("reserved", C.c_int32)]
+                ("min_degree", C.c_int32), ("alpha", C.c_float), ("reserved", C.c_int32)]
 
 
 def library_path():
