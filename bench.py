@@ -412,19 +412,20 @@ def main():
     # optional row-shard exchange (all-gather of per-shard top-k + merge kernel), timed separately
     exchange_ms = None
     if a.shard_rows and world > 1:
-        gi = torch.empty((world, a.batch, a.k), dtype=torch.int64, device=dev)
-        gd = torch.empty((world, a.batch, a.k), dtype=torch.float32, device=dev)
+        from vectordb_b200 import sharded
         mi = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
         md = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
+
+        def merge_fn(all_i, all_d, kk):
+            torch.cuda.synchronize()
+            merge_shards_device(local, all_i.data_ptr(), all_d.data_ptr(), world, a.batch, kk, mi.data_ptr(), md.data_ptr())
+            return mi, md
+
         barrier()
         x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         x0.record()
         for _ in range(a.steps):
-            gl = out_ids + rank * rows
-            dist.all_gather_into_tensor(gi.view(-1), gl.view(-1))
-            dist.all_gather_into_tensor(gd.view(-1), out_d.view(-1))
-            torch.cuda.synchronize()
-            merge_shards_device(local, gi.data_ptr(), gd.data_ptr(), world, a.batch, a.k, mi.data_ptr(), md.data_ptr())
+            sharded.exchange_and_merge(out_ids, out_d, rank * rows, a.k, dist, merge_fn)
         x1.record()
         barrier()
         exchange_ms = x0.elapsed_time(x1) / a.steps
