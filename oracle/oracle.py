@@ -148,13 +148,15 @@ class Port:
 class Ref:
     """The reference itself (VecSearchExecutor / ANNGraphSegment / Expr), via oracle/ref_driver.cpp."""
 
-    def __init__(self, metric, dim, capacity, attr_cols=()):
-        """attr_cols: sequence of (name, type) with type in FIELD_TYPE."""
-        if not have_ref():
-            build()
-        if not have_ref():
-            raise RuntimeError("oracle/_ref/libepsilla_ref.so not available (no /root/reference here and no prebuilt)")
-        L = C.CDLL(REF_SO)
+    def __init__(self, metric, dim, capacity, attr_cols=(), lib_path=None):
+        """attr_cols: sequence of (name, type) with type in FIELD_TYPE.  lib_path: an alternative build of the
+        same driver (integration/_build/libepsilla_ref_b200.so = the reference engine with the GPU drop-in)."""
+        if lib_path is None:
+            if not have_ref():
+                build()
+            if not have_ref():
+                raise RuntimeError("oracle/_ref/libepsilla_ref.so not available (no /root/reference here and no prebuilt)")
+        L = C.CDLL(lib_path or REF_SO)
         L.ref_create.restype = C.c_void_p
         L.ref_create.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_destroy.argtypes = [C.c_void_p]
