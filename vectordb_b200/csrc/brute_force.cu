@@ -360,8 +360,8 @@ __global__ void fill_keys_kernel(unsigned long long* p, int64_t n, unsigned long
 // ------------------------------------------------------------------------------------------------
 // Host driver
 // ------------------------------------------------------------------------------------------------
-static int launch_dist(Index* ix, const float* A_base, int64_t row_start, int64_t n, const float* d_queries,
-                       int64_t nq, float* D, int64_t ldd, uint64_t* launches) {
+int launch_distances(Index* ix, const float* A_base, int64_t row_start, int64_t n, const float* d_queries,
+                     int64_t nq, float* D, int64_t ldd, uint64_t* launches) {
   const int dim = static_cast<int>(ix->dim);
   const bool l2 = ix->metric == EPS_METRIC_L2;
   if (nq <= 16) {
@@ -462,7 +462,7 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
   }
   for (int64_t c0 = 0; c0 < n; c0 += chunk) {
     const int64_t cn = std::min(chunk, n - c0);
-    EPS_TRY(launch_dist(ix, ix->d_vectors, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
+    EPS_TRY(launch_distances(ix, ix->d_vectors, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
     SelectArgs a;
     a.D = D; a.keys_in = nullptr; a.ldd = chunk; a.n = cn; a.row_base = row_start + c0; a.nsplit = nsplit;
     a.k = static_cast<int>(k); a.state = state; a.pass = d_pass; a.pass_base = row_start;

@@ -355,6 +355,8 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
   if (ix->d_offsets) { cudaFree(ix->d_offsets); ix->d_offsets = nullptr; }
   if (ix->d_nbrs) { cudaFree(ix->d_nbrs); ix->d_nbrs = nullptr; }
   if (ix->d_init_ids) { cudaFree(ix->d_init_ids); ix->d_init_ids = nullptr; }
+  if (ix->d_ell) { cudaFree(ix->d_ell); ix->d_ell = nullptr; }
+  ix->seed_rows_L = 0;
   ix->init_L = 0;
   EPS_CUDA(cudaMalloc(&ix->d_offsets, (static_cast<size_t>(n) + 1) * 8));
   EPS_CUDA(cudaMalloc(&ix->d_nbrs, std::max<size_t>(static_cast<size_t>(e), 1) * 4));

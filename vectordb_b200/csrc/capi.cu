@@ -124,6 +124,9 @@ static void free_graph(Index* ix) {
   if (ix->d_offsets) cudaFree(ix->d_offsets);
   if (ix->d_nbrs) cudaFree(ix->d_nbrs);
   if (ix->d_init_ids) cudaFree(ix->d_init_ids);
+  if (ix->d_ell) cudaFree(ix->d_ell);
+  ix->d_ell = nullptr;
+  ix->seed_rows_L = 0;
   ix->d_offsets = nullptr;
   ix->d_nbrs = nullptr;
   ix->d_init_ids = nullptr;
@@ -257,7 +260,7 @@ void eps_index_destroy(eps_index* h) {
   if (ix->d_attrs) cudaFree(ix->d_attrs);
   eps::DevBuf* bufs[] = {&ix->s_queries, &ix->s_dist, &ix->s_topk, &ix->s_topk2, &ix->s_pass, &ix->s_filter,
                          &ix->s_visited, &ix->s_queue, &ix->s_tail, &ix->s_out_ids, &ix->s_out_dists,
-                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc};
+                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist};
   for (auto* b : bufs) b->release();
   for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ix->stream);

@@ -107,40 +107,33 @@ __device__ __forceinline__ float finish_metric(int metric, float acc) {
 template <bool L2>
 __device__ __forceinline__ float lane_partial_vec4(const float* __restrict__ row, const float* __restrict__ q_smem,
                                                    int dim4, int lane) {
+  // All of a lane's 128-bit loads of the row are issued before the first use (up to 6 in flight = 3 KB per
+  // warp), so a 768-d row costs ONE memory round trip instead of one per 64 floats.
   float a0 = 0.f, a1 = 0.f;
-  int c = lane;
-  // two chunks per iteration for ILP
-  for (; c + 32 < dim4; c += 64) {
-    float4 x0 = ldg_f4_stream(row + 4 * c);
-    float4 x1 = ldg_f4_stream(row + 4 * (c + 32));
-    float4 q0 = *reinterpret_cast<const float4*>(q_smem + 4 * c);
-    float4 q1 = *reinterpret_cast<const float4*>(q_smem + 4 * (c + 32));
-    if (L2) {
-      float d;
-      d = x0.x - q0.x; a0 = fmaf(d, d, a0);
-      d = x0.y - q0.y; a0 = fmaf(d, d, a0);
-      d = x0.z - q0.z; a0 = fmaf(d, d, a0);
-      d = x0.w - q0.w; a0 = fmaf(d, d, a0);
-      d = x1.x - q1.x; a1 = fmaf(d, d, a1);
-      d = x1.y - q1.y; a1 = fmaf(d, d, a1);
-      d = x1.z - q1.z; a1 = fmaf(d, d, a1);
-      d = x1.w - q1.w; a1 = fmaf(d, d, a1);
-    } else {
-      a0 = fmaf(x0.x, q0.x, a0); a0 = fmaf(x0.y, q0.y, a0); a0 = fmaf(x0.z, q0.z, a0); a0 = fmaf(x0.w, q0.w, a0);
-      a1 = fmaf(x1.x, q1.x, a1); a1 = fmaf(x1.y, q1.y, a1); a1 = fmaf(x1.z, q1.z, a1); a1 = fmaf(x1.w, q1.w, a1);
+  for (int base = 0; base < dim4; base += 192) {
+    float4 x[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int c = base + u * 32 + lane;
+      if (c < dim4) x[u] = ldg_f4_stream(row + 4 * c);
     }
-  }
-  if (c < dim4) {
-    float4 x0 = ldg_f4_stream(row + 4 * c);
-    float4 q0 = *reinterpret_cast<const float4*>(q_smem + 4 * c);
-    if (L2) {
-      float d;
-      d = x0.x - q0.x; a0 = fmaf(d, d, a0);
-      d = x0.y - q0.y; a0 = fmaf(d, d, a0);
-      d = x0.z - q0.z; a0 = fmaf(d, d, a0);
-      d = x0.w - q0.w; a0 = fmaf(d, d, a0);
-    } else {
-      a0 = fmaf(x0.x, q0.x, a0); a0 = fmaf(x0.y, q0.y, a0); a0 = fmaf(x0.z, q0.z, a0); a0 = fmaf(x0.w, q0.w, a0);
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int c = base + u * 32 + lane;
+      if (c < dim4) {
+        const float4 q = *reinterpret_cast<const float4*>(q_smem + 4 * c);
+        float& acc = (u & 1) ? a1 : a0;
+        if (L2) {
+          float d;
+          d = x[u].x - q.x; acc = fmaf(d, d, acc);
+          d = x[u].y - q.y; acc = fmaf(d, d, acc);
+          d = x[u].z - q.z; acc = fmaf(d, d, acc);
+          d = x[u].w - q.w; acc = fmaf(d, d, acc);
+        } else {
+          acc = fmaf(x[u].x, q.x, acc); acc = fmaf(x[u].y, q.y, acc);
+          acc = fmaf(x[u].z, q.z, acc); acc = fmaf(x[u].w, q.w, acc);
+        }
+      }
     }
   }
   return a0 + a1;

@@ -17,6 +17,8 @@
 // the sorted queue and the query vector in shared memory, one warp per neighbour row (coalesced 128-bit
 // streaming loads, warp-shuffle reduction), a per-CTA visited bitmap in global memory (L2-resident),
 // block-parallel rank-and-shift merge instead of the reference's memmove insert.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace eps {
@@ -48,7 +50,7 @@ __device__ __forceinline__ int lb_masked(const unsigned long long* a, int n, uns
   return lo;
 }
 
-__global__ void __launch_bounds__(128, 8) graph_search_kernel(GSArgs a) {
+__global__ void __launch_bounds__(128, 6) graph_search_kernel(GSArgs a) {
   extern __shared__ __align__(16) unsigned char gs_smem[];
   unsigned long long* queue = reinterpret_cast<unsigned long long*>(gs_smem);          // [Lp]
   unsigned long long* cand = queue + a.Lp;                                             // [kCH] accepted, unsorted
@@ -197,6 +199,228 @@ __global__ void __launch_bounds__(128, 8) graph_search_kernel(GSArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v2 of the kernel: same algorithm and results, restructured against the two stalls the ncu capture of v1
+// showed (profiles/r01_ncu_graph_search_v1_*: barrier 8.4 and long_scoreboard 7.5 per issue, 16 % DRAM):
+//   * fixed-stride adjacency (kEll ids per vertex, -1 padded) => the neighbour ids are ONE load away from the
+//     vertex id (CSR needs offsets first); rows longer than kEll continue in the CSR (rare: repair hubs);
+//   * the adjacency row of the NEXT likely candidate (second unchecked entry) is loaded speculatively by the
+//     otherwise idle warps 2-3 while warps 0-1 run the visited test of the current one;
+//   * the seed distances arrive precomputed as a dense [B x L] tile product (the seed set is query-independent,
+//     SURVEY §8a A4) instead of L warp-per-row evaluations per query;
+//   * the merge shifts in place in super-tiles of 8 keys per thread (2 barriers per 1024 keys instead of per 128);
+//   * a lane issues all 128-bit loads of a row before the first use (one memory round trip per row).
+// Three barriers per expansion when nothing is accepted (the common case late in a search), six otherwise.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kEll = 64;
+
+struct GS2Args {
+  const float* vectors;
+  const int64_t* offsets;
+  const int32_t* nbrs;
+  const int32_t* ell;             // [n x kEll]
+  const int32_t* init_ids;
+  const float* seed_dist;         // [nq x seed_ld]
+  const float* queries;
+  uint32_t* visited;
+  unsigned long long* out_queue;
+  int* work_counter;
+  unsigned long long* stats;
+  int64_t visited_words;
+  int64_t seed_ld;
+  int dim, metric, vec4;
+  int L, Lp;
+  int nq;
+};
+
+__global__ void __launch_bounds__(128, 7) graph_search_kernel_v2(GS2Args a) {
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  unsigned long long* qa = reinterpret_cast<unsigned long long*>(gs_smem);  // [Lp] current queue
+  unsigned long long* cand = qa + a.Lp;                                     // [kCH]
+  unsigned long long* cs = cand + kCH;                                      // [kCH]
+  float* qv = reinterpret_cast<float*>(cs + kCH);                           // [dim4]
+  int* pos = reinterpret_cast<int*>(qv + ((a.dim + 3) & ~3));               // [kCH]
+  int* fresh = pos + kCH;                                                   // [kCH]
+  int* spec = fresh + kCH;                                                  // [2][kEll]
+  __shared__ int s_q, s_cur, s_nfresh, s_nacc, s_pmin, s_more;
+  __shared__ int s_spec_id[2];
+  __shared__ unsigned long long s_ndist, s_nexp, s_nedge;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint32_t* visited = a.visited + static_cast<int64_t>(blockIdx.x) * a.visited_words;
+  const int L = a.L;
+  if (tid == 0) { s_ndist = 0; s_nexp = 0; s_nedge = 0; }
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_q = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int q = s_q;
+    if (q >= a.nq) break;
+    for (int i = tid; i < a.dim; i += blockDim.x) qv[i] = a.queries[static_cast<int64_t>(q) * a.dim + i];
+    for (int i = tid; i < a.Lp; i += blockDim.x) {
+      unsigned long long key = kKeyInf;
+      if (i < L) {
+        const uint32_t id = static_cast<uint32_t>(a.init_ids[i]);
+        atomicOr(&visited[id >> 5], 1u << (id & 31));
+        key = make_key(a.seed_dist[static_cast<int64_t>(q) * a.seed_ld + i], id);
+      }
+      qa[i] = key;
+    }
+    if (tid == 0) { s_nfresh = 0; s_nacc = 0; s_spec_id[0] = -1; s_spec_id[1] = -1; }
+    __syncthreads();
+    block_bitonic_sort(qa, a.Lp);
+
+    int k = 0;
+    for (int it = 0;; ++it) {
+      const int par = it & 1;
+      if (warp == 0) {
+        int found = -1, next = -1;
+        for (int p = k; p < L; p += 32) {
+          const int idx = p + lane;
+          const bool un = idx < L && !(qa[idx] & kCheckedBit);
+          unsigned b = __ballot_sync(kFull, un);
+          if (found < 0 && b) { found = p + __ffs(b) - 1; b &= b - 1; }
+          if (found >= 0 && b) { next = p + __ffs(b) - 1; break; }
+          if (found >= 0 && p >= found + 96) break;  // bounded look-ahead for the speculation
+        }
+        if (lane == 0) {
+          s_cur = found;
+          s_pmin = L;
+          s_more = 0;
+          if (found >= 0) qa[found] |= kCheckedBit;
+          s_spec_id[par] = next >= 0 ? static_cast<int>(key_id(qa[next])) : -1;
+        }
+      }
+      __syncthreads();  // (1)
+      const int cur = s_cur;
+      if (cur < 0) break;
+      const int c = static_cast<int>(key_id(qa[cur]));
+      const bool hit = s_spec_id[par ^ 1] == c;
+      if (tid < kEll) {
+        const int nb = hit ? spec[(par ^ 1) * kEll + tid] : __ldg(a.ell + static_cast<int64_t>(c) * kEll + tid);
+        if (nb >= 0) {
+          const uint32_t bit = 1u << (nb & 31);
+          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
+          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = nb;
+          if (tid == kEll - 1) s_more = 1;  // full row: it may continue in the CSR
+        }
+        const unsigned vb = __ballot_sync(kFull, nb >= 0);
+        if (lane == 0 && vb) atomicAdd(&s_nedge, static_cast<unsigned long long>(__popc(vb)));
+      } else {
+        const int c2 = s_spec_id[par];
+        if (c2 >= 0) spec[par * kEll + (tid - kEll)] = __ldg(a.ell + static_cast<int64_t>(c2) * kEll + (tid - kEll));
+      }
+      __syncthreads();  // (2)
+      int64_t e_next = 0, e_end = 0;
+      if (s_more) { e_next = a.offsets[c] + kEll; e_end = a.offsets[c + 1]; }
+      if (tid == 0) { ++s_nexp; }
+      for (;;) {
+        const int nfresh = s_nfresh;
+        const unsigned long long bound = qa[L - 1] & kKeyMask;
+        for (int i = warp; i < nfresh; i += nwarps) {
+          const int nb = fresh[i];
+          float d = warp_distance(a.metric, a.vec4 != 0, a.vectors + static_cast<int64_t>(nb) * a.dim, qv, a.dim, lane);
+          if (lane == 0) {
+            const unsigned long long key = make_key(d, static_cast<uint32_t>(nb));
+            if (key < bound) cand[atomicAdd(&s_nacc, 1)] = key;
+          }
+        }
+        __syncthreads();  // (3)
+        const int m = s_nacc;
+        if (m > 0) {
+          for (int i = tid; i < m; i += blockDim.x) {
+            const unsigned long long key = cand[i];
+            int r = 0;
+            for (int j = 0; j < m; ++j) r += (cand[j] < key);
+            cs[r] = key;
+          }
+          __syncthreads();
+          for (int i = tid; i < m; i += blockDim.x) pos[i] = lb_masked(qa, L, cs[i]);
+          __syncthreads();
+          const int p0 = pos[0];
+          // in-place shift of [p0, L): super-tiles of 8 keys per thread, top first; each key moves right by
+          // the number of accepted candidates that precede it (counted linearly: m is small)
+          for (int hi = L; hi > p0; hi -= 8 * 128) {
+            unsigned long long kreg[8];
+            int dreg[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = hi - 1 - (u * 128 + tid);
+              dreg[u] = L;
+              if (j >= p0) {
+                kreg[u] = qa[j];
+                int sft = 0;
+                if (m <= 8) { for (int i = 0; i < m; ++i) sft += (pos[i] <= j); }
+                else { int lo = 0, up = m; while (lo < up) { const int mid = (lo + up) >> 1; if (pos[mid] <= j) lo = mid + 1; else up = mid; } sft = lo; }
+                dreg[u] = j + sft;
+              }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (dreg[u] < L) qa[dreg[u]] = kreg[u];
+            __syncthreads();
+          }
+          for (int i = tid; i < m; i += blockDim.x) {
+            const int f = pos[i] + i;
+            if (f < L) qa[f] = cs[i];
+          }
+          if (tid == 0 && p0 < s_pmin) s_pmin = p0;
+        }
+        if (tid == 0) { s_ndist += static_cast<unsigned long long>(nfresh); s_nfresh = 0; s_nacc = 0; }
+        __syncthreads();  // queue + counters settled
+        if (e_next >= e_end) break;
+        // rare: the row continues in the CSR beyond its first kEll entries
+        const int cnt = static_cast<int>(min(static_cast<int64_t>(kCH), e_end - e_next));
+        if (tid < cnt) {
+          const uint32_t nb = static_cast<uint32_t>(a.nbrs[e_next + tid]);
+          const uint32_t bit = 1u << (nb & 31);
+          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
+          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = static_cast<int>(nb);
+        }
+        e_next += cnt;
+        __syncthreads();
+      }
+      const int pmin = s_pmin;
+      k = (pmin <= k) ? pmin : k + 1;
+    }
+
+    unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
+    for (int i = tid; i < L; i += blockDim.x) out[i] = qa[i];
+    {
+      uint4* v4 = reinterpret_cast<uint4*>(visited);
+      const int64_t n4 = a.visited_words >> 2;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int64_t i = tid; i < n4; i += blockDim.x) v4[i] = z;
+    }
+    if (tid == 0) s_ndist += static_cast<unsigned long long>(L);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(&a.stats[0], s_ndist);
+    atomicAdd(&a.stats[1], s_nexp);
+    atomicAdd(&a.stats[2], s_nedge);
+  }
+}
+
+__global__ void csr_to_ell_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbrs, int64_t n,
+                                  int32_t* __restrict__ ell) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n * kEll) return;
+  const int64_t v = i / kEll;
+  const int s = static_cast<int>(i % kEll);
+  const int64_t e = offsets[v] + s;
+  ell[i] = e < offsets[v + 1] ? nbrs[e] : -1;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ vectors, const int32_t* __restrict__ ids, int n, int dim,
+                                   float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(n) * dim) return;
+  const int r = static_cast<int>(i / dim), c = static_cast<int>(i % dim);
+  out[i] = vectors[static_cast<int64_t>(ids[r]) * dim + c];
+}
+
 // PrepareInitIds (vec_search_executor.cpp:487-516): dedup'd out-neighbours of the navigation point, then
 // ids nav+1, nav+2, ... (mod n) until L entries.  Pure index logic on <= L + deg entries; runs on the host
 // over the navigation row copied back from the device.  L is clamped to n_indexed by the caller (the
@@ -243,11 +467,18 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   if (Lp > 16384) return fail(EPS_ERR_UNSUPPORTED, "SearchQueueSize above 16384 is not supported by the graph kernel");
   EPS_TRY(prepare_init_ids(ix, L));
   const int dimp = (static_cast<int>(ix->dim) + 3) & ~3;
-  const size_t smem = static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4;
+  const bool use_v2 = getenv("EPS_GRAPH_V1") == nullptr;
+  const size_t smem = use_v2 ? static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4 + 2 * kEll * 4
+                             : static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4;
   if (smem > 220 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query do not fit in shared memory");
-  EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
-  EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel, 128, smem));
+  if (use_v2) {
+    EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel_v2, 128, smem));
+  } else {
+    EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel, 128, smem));
+  }
   if (per_sm < 1) per_sm = 1;
   int slots = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(per_sm) * ix->num_sms));
   const int64_t words = ((ix->n_indexed + 31) / 32 + 3) & ~3ll;
@@ -263,18 +494,50 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   }
   EPS_TRY(ix->s_misc.reserve(64));
   EPS_CUDA(cudaMemsetAsync(ix->s_misc.p, 0, 64, ix->stream));
-  GSArgs a;
-  a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.init_ids = ix->d_init_ids;
-  a.queries = d_queries; a.visited = ix->s_visited.as<uint32_t>(); a.out_queue = d_queue;
-  a.work_counter = reinterpret_cast<int*>(ix->s_misc.as<unsigned char>() + 32);
-  a.stats = ix->s_misc.as<unsigned long long>();
-  a.visited_words = words; a.dim = static_cast<int>(ix->dim); a.metric = ix->metric; a.vec4 = ix->vec4 ? 1 : 0;
-  a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
-  graph_search_kernel<<<slots, 128, smem, ix->stream>>>(a);
+  uint64_t launches = 1;
+  if (use_v2) {
+    if (!ix->d_ell) {  // fixed-stride adjacency, built once per installed graph
+      EPS_CUDA(cudaMalloc(&ix->d_ell, static_cast<size_t>(ix->n_indexed) * kEll * 4));
+      const int64_t tot = ix->n_indexed * kEll;
+      csr_to_ell_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(ix->d_offsets, ix->d_nbrs,
+                                                                                          ix->n_indexed, ix->d_ell);
+      EPS_CUDA(cudaGetLastError());
+    }
+    if (ix->seed_rows_L != L) {  // contiguous copy of the query-independent seed rows
+      EPS_TRY(ix->s_seed_rows.reserve(static_cast<size_t>(L) * ix->dim * 4));
+      const int64_t tot = L * ix->dim;
+      gather_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(
+          ix->d_vectors, ix->d_init_ids, static_cast<int>(L), static_cast<int>(ix->dim), ix->s_seed_rows.as<float>());
+      EPS_CUDA(cudaGetLastError());
+      ix->seed_rows_L = L;
+    }
+    const int64_t seed_ld = (L + 3) & ~3ll;
+    EPS_TRY(ix->s_seed_dist.reserve(static_cast<size_t>(nq) * seed_ld * 4));
+    EPS_TRY(launch_distances(ix, ix->s_seed_rows.as<float>(), 0, L, d_queries, nq, ix->s_seed_dist.as<float>(), seed_ld,
+                             &launches));
+    GS2Args a;
+    a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.ell = ix->d_ell;
+    a.init_ids = ix->d_init_ids; a.seed_dist = ix->s_seed_dist.as<float>(); a.queries = d_queries;
+    a.visited = ix->s_visited.as<uint32_t>(); a.out_queue = d_queue;
+    a.work_counter = reinterpret_cast<int*>(ix->s_misc.as<unsigned char>() + 32);
+    a.stats = ix->s_misc.as<unsigned long long>();
+    a.visited_words = words; a.seed_ld = seed_ld; a.dim = static_cast<int>(ix->dim); a.metric = ix->metric;
+    a.vec4 = ix->vec4 ? 1 : 0; a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
+    graph_search_kernel_v2<<<slots, 128, smem, ix->stream>>>(a);
+  } else {
+    GSArgs a;
+    a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.init_ids = ix->d_init_ids;
+    a.queries = d_queries; a.visited = ix->s_visited.as<uint32_t>(); a.out_queue = d_queue;
+    a.work_counter = reinterpret_cast<int*>(ix->s_misc.as<unsigned char>() + 32);
+    a.stats = ix->s_misc.as<unsigned long long>();
+    a.visited_words = words; a.dim = static_cast<int>(ix->dim); a.metric = ix->metric; a.vec4 = ix->vec4 ? 1 : 0;
+    a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
+    graph_search_kernel<<<slots, 128, smem, ix->stream>>>(a);
+  }
   EPS_CUDA(cudaGetLastError());
   if (stats) {
     stats->n_seed += static_cast<uint64_t>(nq) * static_cast<uint64_t>(L);
-    stats->kernel_launches += 1;
+    stats->kernel_launches += launches;
   }
   return EPS_OK;
 }

@@ -39,6 +39,8 @@ struct Index {
   int32_t* d_nbrs = nullptr;     // [n_edges]
   int32_t* d_init_ids = nullptr; // seed set for init_L
   int64_t init_L = 0;
+  int32_t* d_ell = nullptr;      // fixed-stride adjacency [n_indexed x 64] (-1 padded), built lazily
+  int64_t seed_rows_L = 0;       // L for which s_seed_rows holds the gathered seed rows
 
   // segment mirrors
   uint8_t* d_deleted = nullptr;
@@ -59,7 +61,7 @@ struct Index {
 
   // scratch
   DevBuf s_queries, s_dist, s_topk, s_topk2, s_pass, s_filter, s_visited, s_queue, s_tail, s_out_ids, s_out_dists,
-      s_out_counts, s_stats, s_misc;
+      s_out_counts, s_stats, s_misc, s_seed_rows, s_seed_dist;
   int64_t visited_slots = 0;
   const void* vis_clean_ptr = nullptr;  // geometry for which the visited bitmaps are known to be zero
   int64_t vis_clean_words = 0;
@@ -73,6 +75,11 @@ struct Index {
 int brute_force_topk(Index* ix, const float* d_queries, int64_t nq, int64_t row_start, int64_t row_end, int64_t k,
                      const FilterProg* d_prog, const FilterProg* h_prog, bool prefilter, unsigned long long* d_topk,
                      eps_stats* stats);
+
+// Distances of rows [row_start,row_start+n) of A_base to nq device queries: D[q*ldd + i] (row kernel for
+// nq <= 16, 128x128 tile kernel otherwise).
+int launch_distances(Index* ix, const float* A_base, int64_t row_start, int64_t n, const float* d_queries, int64_t nq,
+                     float* D, int64_t ldd, uint64_t* launches);
 
 // All-pairs variant used by the graph build: for queries = rows [q_start, q_start+nq) of the table.
 int brute_force_knn_rows(Index* ix, int64_t q_start, int64_t nq, int64_t n_rows, int64_t k,
