@@ -358,6 +358,36 @@ __global__ void fill_keys_kernel(unsigned long long* p, int64_t n, unsigned long
 }
 
 // ------------------------------------------------------------------------------------------------
+// Exact re-score of the coarse (tensor-core) candidates: one CTA per query, one warp per candidate, the fp32
+// direct form of the reference; then the final (distance,id) sort.  coarse [nq x kc] -> out [nq x k].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rescore_kernel(const float* __restrict__ vectors, int dim, int metric, int vec4,
+                                                     const float* __restrict__ queries,
+                                                     const unsigned long long* __restrict__ coarse, int kc, int kcp, int k,
+                                                     unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(rs_smem);  // [kcp]
+  float* qv = reinterpret_cast<float*>(keys + kcp);
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < dim; i += blockDim.x) qv[i] = queries[static_cast<int64_t>(q) * dim + i];
+  for (int i = kc + tid; i < kcp; i += blockDim.x) keys[i] = kKeyInf;
+  __syncthreads();
+  for (int c = warp; c < kc; c += 4) {
+    const unsigned long long ck = coarse[static_cast<int64_t>(q) * kc + c];
+    unsigned long long key = kKeyInf;
+    if ((ck & kKeyMask) != kKeyInf) {
+      const uint32_t id = key_id(ck);
+      const float d = warp_distance(metric, vec4 != 0, vectors + static_cast<int64_t>(id) * dim, qv, dim, lane);
+      key = make_key(d, id);
+    }
+    if (lane == 0) keys[c] = key;
+  }
+  __syncthreads();
+  block_bitonic_sort(keys, kcp);
+  for (int i = tid; i < k; i += blockDim.x) out[static_cast<int64_t>(q) * k + i] = keys[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host driver
 // ------------------------------------------------------------------------------------------------
 int launch_distances(Index* ix, const float* A_base, int64_t row_start, int64_t n, const float* d_queries,
@@ -408,6 +438,17 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
   if (k < 1 || k > 8192) return fail(EPS_ERR_UNSUPPORTED, "brute-force top-k supports 1 <= k <= 8192");
   uint64_t launches = 0;
   const int64_t n = row_end - row_start;
+  // Tensor-core coarse pass + exact re-score (tc_dist.cu) for large batches; a filter that reads the real
+  // distance needs exact values inside the select and stays on the fp32 SIMT path.
+  const bool dyn_filter = h_prog && h_prog->n > 0 && !prefilter && h_prog->root_uses_dist;
+  const int64_t k_final = k;
+  unsigned long long* d_final = d_topk;
+  const bool use_tc = n >= 4096 && self_base < 0 && !dyn_filter && tc_dist_usable(ix, nq) && d_queries != ix->d_vectors;
+  if (use_tc) {
+    k = std::min<int64_t>(8192, k_final + std::max<int64_t>(32, k_final));
+    EPS_TRY(ix->s_coarse.reserve(static_cast<size_t>(nq) * k * 8));
+    d_topk = ix->s_coarse.as<unsigned long long>();
+  }
   {
     int64_t tot = nq * k;
     fill_keys_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(d_topk, tot, kKeyInf);
@@ -462,7 +503,8 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
   }
   for (int64_t c0 = 0; c0 < n; c0 += chunk) {
     const int64_t cn = std::min(chunk, n - c0);
-    EPS_TRY(launch_distances(ix, ix->d_vectors, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
+    if (use_tc) EPS_TRY(tc_launch_distances(ix, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
+    else EPS_TRY(launch_distances(ix, ix->d_vectors, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
     SelectArgs a;
     a.D = D; a.keys_in = nullptr; a.ldd = chunk; a.n = cn; a.row_base = row_start + c0; a.nsplit = nsplit;
     a.k = static_cast<int>(k); a.state = state; a.pass = d_pass; a.pass_base = row_start;
@@ -480,6 +522,17 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     bf_select_kernel<true><<<dim3(static_cast<unsigned>(nq), 1), kSelThreads, sel_smem, ix->stream>>>(a);
     ++launches;
     EPS_CUDA(cudaGetLastError());
+  }
+  if (use_tc) {
+    const int kc = static_cast<int>(k), kcp = next_pow2(kc);
+    const size_t rs_smem = static_cast<size_t>(kcp) * 8 + static_cast<size_t>((ix->dim + 3) & ~3ll) * 4;
+    if (rs_smem > 48 * 1024)
+      EPS_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem)));
+    rescore_kernel<<<static_cast<unsigned>(nq), 128, rs_smem, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), ix->metric,
+                                                                          ix->vec4 ? 1 : 0, d_queries, d_topk, kc, kcp,
+                                                                          static_cast<int>(k_final), d_final);
+    EPS_CUDA(cudaGetLastError());
+    ++launches;
   }
   if (stats) {
     stats->n_dist += static_cast<uint64_t>(nq) * static_cast<uint64_t>(n);

@@ -260,7 +260,7 @@ void eps_index_destroy(eps_index* h) {
   if (ix->d_attrs) cudaFree(ix->d_attrs);
   eps::DevBuf* bufs[] = {&ix->s_queries, &ix->s_dist, &ix->s_topk, &ix->s_topk2, &ix->s_pass, &ix->s_filter,
                          &ix->s_visited, &ix->s_queue, &ix->s_tail, &ix->s_out_ids, &ix->s_out_dists,
-                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist};
+                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist, &ix->s_xnorm, &ix->s_qnorm, &ix->s_coarse};
   for (auto* b : bufs) b->release();
   for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ix->stream);

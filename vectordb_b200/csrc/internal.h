@@ -61,7 +61,9 @@ struct Index {
 
   // scratch
   DevBuf s_queries, s_dist, s_topk, s_topk2, s_pass, s_filter, s_visited, s_queue, s_tail, s_out_ids, s_out_dists,
-      s_out_counts, s_stats, s_misc, s_seed_rows, s_seed_dist;
+      s_out_counts, s_stats, s_misc, s_seed_rows, s_seed_dist, s_xnorm, s_qnorm, s_coarse;
+  int64_t xnorm_rows = 0;        // rows whose |x|^2 is current in s_xnorm
+  const void* xnorm_ptr = nullptr;
   int64_t visited_slots = 0;
   const void* vis_clean_ptr = nullptr;  // geometry for which the visited bitmaps are known to be zero
   int64_t vis_clean_words = 0;
@@ -80,6 +82,11 @@ int brute_force_topk(Index* ix, const float* d_queries, int64_t nq, int64_t row_
 // nq <= 16, 128x128 tile kernel otherwise).
 int launch_distances(Index* ix, const float* A_base, int64_t row_start, int64_t n, const float* d_queries, int64_t nq,
                      float* D, int64_t ldd, uint64_t* launches);
+
+// tc_dist.cu: tcgen05 TF32 coarse distances (same contract as launch_distances, values carry ~1e-3 rel. error)
+bool tc_dist_usable(const Index* ix, int64_t nq);
+int tc_launch_distances(Index* ix, int64_t row_start, int64_t n, const float* d_queries, int64_t nq, float* D, int64_t ldd,
+                        uint64_t* launches);
 
 // All-pairs variant used by the graph build: for queries = rows [q_start, q_start+nq) of the table.
 int brute_force_knn_rows(Index* ix, int64_t q_start, int64_t nq, int64_t n_rows, int64_t k,
