@@ -136,6 +136,13 @@ EPS_API int eps_index_set_attrs(eps_index* ix, const char* attribute_table, int6
  * search an exact scan (what the reference does for un-indexed tables). */
 EPS_API int eps_index_config(eps_index* ix, int64_t L_master, int64_t L_local, int prefilter, int force_brute);
 
+/* Precision of the COARSE pass of large-batch exact scans (nq >= 64): 0 = none (fp32 SIMT tiles only),
+ * 1 = tcgen05 kind::tf32 on the fp32 rows (default), 2 = tcgen05 kind::f16 on a bf16 mirror of the table
+ * (+50 % HBM).  Whatever the mode, the k + max(32, k) best coarse candidates of every query are re-evaluated
+ * with the exact fp32 direct form, so returned distances are fp32-exact and ids differ from mode 0 only if a
+ * true top-k row fell outside the coarse candidate list. */
+EPS_API int eps_index_set_coarse(eps_index* ix, int mode);
+
 /* ---------------------------------------------------------------------------------------------
  * Search.  Replaces VecSearchExecutor::Search (db/execution/vec_search_executor.cpp:833-935),
  * batched: query i's results are out_ids[i*limit .. i*limit+out_counts[i]) (internal row ids,

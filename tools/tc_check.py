@@ -14,6 +14,7 @@ def run(rows, dim, nq, k, metric):
     ix = vectordb_b200.Index(metric, dim, capacity=rows)
     ix.adopt_device_rows(X.data_ptr(), rows)
     ix.config(512, 512, force_brute=True)
+    ix.set_coarse(os.environ.get("EPS_COARSE", "tf32"))
     oi = torch.empty((nq, k), dtype=torch.int64, device=dev); od = torch.empty((nq, k), dtype=torch.float32, device=dev)
     oc = torch.empty((nq,), dtype=torch.int64, device=dev)
     for _ in range(2):
@@ -27,10 +28,10 @@ if __name__ == "__main__":
         np.savez(sys.argv[7], ids=ids, ds=ds, ms=ms)
         sys.exit(0)
     cases = [(20000, 64, 256, 10, "l2"), (50000, 768, 1024, 10, "l2"), (33333, 100, 300, 100, "ip"), (40000, 128, 512, 10, "cosine"),
-             (1000000, 768, 1024, 10, "l2")]
+             (1000000, 768, 1024, 10, "l2"), (4000000, 768, 1024, 10, "l2")]
     for c in cases:
         out = {}
-        for tag, env in (("tc", {}), ("simt", {"EPS_NO_TC": "1"})):
+        for tag, env in (("tc", {"EPS_COARSE": "tf32"}), ("bf16", {"EPS_COARSE": "bf16"}), ("simt", {"EPS_COARSE": "fp32"})):
             f = "/tmp/tc_%s.npz" % tag
             e = dict(os.environ); e.update(env)
             r = subprocess.run(["timeout", "120", sys.executable, __file__, "child"] + [str(x) for x in c] + [f], env=e,
@@ -40,7 +41,9 @@ if __name__ == "__main__":
             out[tag] = np.load(f)
         if out is None:
             continue
-        same = float((out["tc"]["ids"] == out["simt"]["ids"]).mean())
-        rel = float(np.max(np.abs(out["tc"]["ds"] - out["simt"]["ds"]) / np.maximum(np.abs(out["simt"]["ds"]), 1e-6)))
-        print(json.dumps({"case": c, "ids_equal": same, "max_rel_dist_diff": rel, "tc_ms": float(out["tc"]["ms"]),
-                          "simt_ms": float(out["simt"]["ms"])}))
+        res = {"case": c, "simt_ms": round(float(out["simt"]["ms"]), 3)}
+        for t in ("tc", "bf16"):
+            res[t + "_ids_equal"] = float((out[t]["ids"] == out["simt"]["ids"]).mean())
+            res[t + "_set_recall"] = float(np.mean([len(set(a) & set(b)) / len(b) for a, b in zip(out[t]["ids"], out["simt"]["ids"])]))
+            res[t + "_ms"] = round(float(out[t]["ms"]), 3)
+        print(json.dumps(res))

@@ -283,6 +283,9 @@ struct SelectArgs {
   const char* attrs;
   int64_t attr_stride;
   int64_t self_base;         // query q is row self_base + q and is excluded (-1: off)
+  const int* counts;         // KEYS_IN: valid keys per query (<= n), null = n
+  float* thr_out;            // if set: distance of the k-th entry after this pass (running threshold)
+  int* overflow;             // if set: raised when counts[q] > n (candidates were dropped)
 };
 
 template <bool KEYS_IN>
@@ -299,9 +302,14 @@ __global__ void __launch_bounds__(kSelThreads) bf_select_kernel(SelectArgs a) {
   if (threadIdx.x == 0) nbuf = 0;
   __syncthreads();
   unsigned long long thr = topk[a.k - 1] & kKeyMask;
-  const int64_t per = (a.n + a.nsplit - 1) / a.nsplit;
+  int64_t n_here = a.n;
+  if (KEYS_IN && a.counts) {
+    const int c = a.counts[q];
+    if (c > a.n) { if (a.overflow && threadIdx.x == 0) *a.overflow = 1; } else n_here = c;
+  }
+  const int64_t per = (n_here + a.nsplit - 1) / a.nsplit;
   const int64_t begin = split * per;
-  const int64_t end = min(a.n, begin + per);
+  const int64_t end = min(n_here, begin + per);
   for (int64_t base = begin; base < end; base += kSelRound) {
 #pragma unroll
     for (int it = 0; it < kSelItems; ++it) {
@@ -350,6 +358,10 @@ __global__ void __launch_bounds__(kSelThreads) bf_select_kernel(SelectArgs a) {
     if (n > 0) select_flush(topk, merged, buf, n, a.k);
   }
   for (int j = threadIdx.x; j < a.k; j += blockDim.x) st[j] = topk[j];
+  if (a.thr_out && threadIdx.x == 0 && split == 0) {
+    const unsigned long long w = topk[a.k - 1];
+    a.thr_out[q] = ((w & kKeyMask) == kKeyInf) ? INFINITY : key_dist(w);
+  }
 }
 
 __global__ void fill_keys_kernel(unsigned long long* p, int64_t n, unsigned long long v) {
@@ -434,7 +446,7 @@ int launch_distances(Index* ix, const float* A_base, int64_t row_start, int64_t 
 
 static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_start, int64_t row_end, int64_t k,
                      const FilterProg* d_prog, const FilterProg* h_prog, bool prefilter, int64_t self_base,
-                     unsigned long long* d_topk, eps_stats* stats) {
+                     unsigned long long* d_topk, eps_stats* stats, bool allow_tc = true) {
   if (k < 1 || k > 8192) return fail(EPS_ERR_UNSUPPORTED, "brute-force top-k supports 1 <= k <= 8192");
   uint64_t launches = 0;
   const int64_t n = row_end - row_start;
@@ -443,7 +455,7 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
   const bool dyn_filter = h_prog && h_prog->n > 0 && !prefilter && h_prog->root_uses_dist;
   const int64_t k_final = k;
   unsigned long long* d_final = d_topk;
-  const bool use_tc = n >= 4096 && self_base < 0 && !dyn_filter && tc_dist_usable(ix, nq) && d_queries != ix->d_vectors;
+  const bool use_tc = allow_tc && n >= 4096 && self_base < 0 && !dyn_filter && tc_dist_usable(ix, nq) && d_queries != ix->d_vectors;
   if (use_tc) {
     k = std::min<int64_t>(8192, k_final + std::max<int64_t>(32, k_final));
     EPS_TRY(ix->s_coarse.reserve(static_cast<size_t>(nq) * k * 8));
@@ -487,6 +499,7 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     int64_t want = (2ll * ix->num_sms + nq - 1) / nq;
     int64_t maxs = std::max<int64_t>(1, chunk / 4096);
     nsplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, maxs), 64)));
+    if (use_tc) nsplit = 1;  // the running threshold is read from the single per-query state
   }
   unsigned long long* state = d_topk;
   if (nsplit > 1) {
@@ -501,24 +514,64 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     EPS_CUDA(cudaFuncSetAttribute(bf_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
     EPS_CUDA(cudaFuncSetAttribute(bf_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
   }
-  for (int64_t c0 = 0; c0 < n; c0 += chunk) {
-    const int64_t cn = std::min(chunk, n - c0);
-    if (use_tc) EPS_TRY(tc_launch_distances(ix, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
-    else EPS_TRY(launch_distances(ix, ix->d_vectors, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
+  const int cand_cap = 4096;
+  int* d_overflow = nullptr;
+  if (use_tc) {
+    EPS_TRY(ix->s_thr.reserve(static_cast<size_t>(nq) * 4));
+    EPS_TRY(ix->s_cand.reserve(static_cast<size_t>(nq) * cand_cap * 8));
+    EPS_TRY(ix->s_cand_cnt.reserve(static_cast<size_t>(nq + 1) * 4));
+    d_overflow = ix->s_cand_cnt.as<int>() + nq;
+    EPS_CUDA(cudaMemsetAsync(d_overflow, 0, 4, ix->stream));
+  }
+  for (int64_t c0 = 0; c0 < n;) {
+    // Chunk 0 (and every chunk of the SIMT path) materialises the [nq x chunk] distance tile and selects from
+    // it; it also seeds the per-query running threshold.  Later tensor-core chunks filter against that
+    // threshold inside the epilogue (no distance tile leaves the SM) and only the few survivors are merged.
+    const bool fused = use_tc && c0 > 0;
+    // tensor-core mode: a small first chunk (it pays the distance-tile round trip), then fused launches that grow
+    // as the thresholds tighten (expected survivors per query ~ k' * rows_in_launch / rows_seen_so_far)
+    int64_t want_rows = chunk;
+    if (use_tc) want_rows = fused ? std::min<int64_t>(std::max<int64_t>(4 * c0, 512 * 1024), 4 * 1024 * 1024)
+                                  : std::min<int64_t>(chunk, 128 * 1024);
+    const int64_t cn = std::min(want_rows, n - c0);
     SelectArgs a;
-    a.D = D; a.keys_in = nullptr; a.ldd = chunk; a.n = cn; a.row_base = row_start + c0; a.nsplit = nsplit;
-    a.k = static_cast<int>(k); a.state = state; a.pass = d_pass; a.pass_base = row_start;
-    a.dyn = dynamic ? d_prog : nullptr; a.attrs = ix->d_attrs; a.attr_stride = ix->attr_stride;
-    a.self_base = self_base;
-    bf_select_kernel<false><<<dim3(static_cast<unsigned>(nq), nsplit), kSelThreads, sel_smem, ix->stream>>>(a);
+    a.ldd = chunk; a.row_base = row_start + c0; a.nsplit = nsplit; a.k = static_cast<int>(k); a.state = state;
+    a.pass = d_pass; a.pass_base = row_start; a.dyn = dynamic ? d_prog : nullptr; a.attrs = ix->d_attrs;
+    a.attr_stride = ix->attr_stride; a.self_base = self_base; a.counts = nullptr; a.overflow = nullptr;
+    a.thr_out = use_tc ? ix->s_thr.as<float>() : nullptr;
+    if (!fused) {
+      if (use_tc) EPS_TRY(tc_launch_distances(ix, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
+      else EPS_TRY(launch_distances(ix, ix->d_vectors, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
+      a.D = D; a.keys_in = nullptr; a.n = cn;
+      bf_select_kernel<false><<<dim3(static_cast<unsigned>(nq), nsplit), kSelThreads, sel_smem, ix->stream>>>(a);
+    } else {
+      EPS_CUDA(cudaMemsetAsync(ix->s_cand_cnt.p, 0, static_cast<size_t>(nq) * 4, ix->stream));
+      TcFused f;
+      f.thr = ix->s_thr.as<float>(); f.cand = ix->s_cand.as<unsigned long long>(); f.cand_cnt = ix->s_cand_cnt.as<int>();
+      f.pass = d_pass; f.pass_base = row_start; f.cand_cap = cand_cap;
+      EPS_TRY(tc_launch_distances(ix, row_start + c0, cn, d_queries, nq, nullptr, 0, &launches, &f));
+      a.D = nullptr; a.keys_in = f.cand; a.n = cand_cap; a.counts = f.cand_cnt; a.overflow = d_overflow;
+      a.pass = nullptr; a.dyn = nullptr;
+      bf_select_kernel<true><<<dim3(static_cast<unsigned>(nq), 1), kSelThreads, sel_smem, ix->stream>>>(a);
+    }
     ++launches;
     EPS_CUDA(cudaGetLastError());
+    c0 += cn;
+  }
+  if (use_tc) {
+    // candidate buffers are sized for the expected k'/c survivors per query; an adversarial row order can
+    // overflow them — detected here, and the call is redone on the fp32 path (never silently truncated)
+    int h_overflow = 0;
+    EPS_CUDA(cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, ix->stream));
+    EPS_CUDA(cudaStreamSynchronize(ix->stream));
+    if (h_overflow)
+      return topk_impl(ix, d_queries, nq, row_start, row_end, k_final, d_prog, h_prog, prefilter, self_base, d_final, stats, false);
   }
   if (nsplit > 1) {
     SelectArgs a;
     a.D = nullptr; a.keys_in = state; a.ldd = 0; a.n = static_cast<int64_t>(nsplit) * k; a.row_base = 0; a.nsplit = 1;
     a.k = static_cast<int>(k); a.state = d_topk; a.pass = nullptr; a.pass_base = 0; a.dyn = nullptr;
-    a.attrs = nullptr; a.attr_stride = 0; a.self_base = -1;
+    a.attrs = nullptr; a.attr_stride = 0; a.self_base = -1; a.counts = nullptr; a.thr_out = nullptr; a.overflow = nullptr;
     bf_select_kernel<true><<<dim3(static_cast<unsigned>(nq), 1), kSelThreads, sel_smem, ix->stream>>>(a);
     ++launches;
     EPS_CUDA(cudaGetLastError());

@@ -260,7 +260,7 @@ void eps_index_destroy(eps_index* h) {
   if (ix->d_attrs) cudaFree(ix->d_attrs);
   eps::DevBuf* bufs[] = {&ix->s_queries, &ix->s_dist, &ix->s_topk, &ix->s_topk2, &ix->s_pass, &ix->s_filter,
                          &ix->s_visited, &ix->s_queue, &ix->s_tail, &ix->s_out_ids, &ix->s_out_dists,
-                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist, &ix->s_xnorm, &ix->s_qnorm, &ix->s_coarse};
+                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist, &ix->s_xnorm, &ix->s_qnorm, &ix->s_coarse, &ix->s_thr, &ix->s_cand, &ix->s_cand_cnt, &ix->s_bf16, &ix->s_qbf16};
   for (auto* b : bufs) b->release();
   for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ix->stream);
@@ -485,6 +485,14 @@ int eps_pair_distances(int device, int metric, const float* a, const float* b, i
   cudaMemcpy(out, dout, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost);
   cudaFree(da); cudaFree(db); cudaFree(dout);
   if (e != cudaSuccess) return eps::fail(EPS_ERR_CUDA, cudaGetErrorString(e));
+  return EPS_OK;
+}
+
+int eps_index_set_coarse(eps_index* h, int mode) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  if (mode < 0 || mode > 2) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "coarse mode must be 0 (fp32), 1 (tf32) or 2 (bf16)");
+  ix->coarse_mode = mode;
   return EPS_OK;
 }
 

@@ -61,7 +61,10 @@ struct Index {
 
   // scratch
   DevBuf s_queries, s_dist, s_topk, s_topk2, s_pass, s_filter, s_visited, s_queue, s_tail, s_out_ids, s_out_dists,
-      s_out_counts, s_stats, s_misc, s_seed_rows, s_seed_dist, s_xnorm, s_qnorm, s_coarse;
+      s_out_counts, s_stats, s_misc, s_seed_rows, s_seed_dist, s_xnorm, s_qnorm, s_coarse, s_thr, s_cand, s_cand_cnt, s_bf16, s_qbf16;
+  int coarse_mode = 1;           // exact-scan coarse pass: 0 = fp32 SIMT only, 1 = tcgen05 TF32, 2 = tcgen05 bf16 mirror
+  int64_t bf16_rows = 0;
+  const void* bf16_ptr = nullptr;
   int64_t xnorm_rows = 0;        // rows whose |x|^2 is current in s_xnorm
   const void* xnorm_ptr = nullptr;
   int64_t visited_slots = 0;
@@ -85,8 +88,16 @@ int launch_distances(Index* ix, const float* A_base, int64_t row_start, int64_t 
 
 // tc_dist.cu: tcgen05 TF32 coarse distances (same contract as launch_distances, values carry ~1e-3 rel. error)
 bool tc_dist_usable(const Index* ix, int64_t nq);
+struct TcFused {             // fused threshold selection in the epilogue (no distance tile written)
+  const float* thr;          // [nq] running coarse k'-th best
+  unsigned long long* cand;  // [nq x cand_cap]
+  int* cand_cnt;             // [nq], zeroed by the caller
+  const uint32_t* pass;      // may be null
+  int64_t pass_base;
+  int cand_cap;
+};
 int tc_launch_distances(Index* ix, int64_t row_start, int64_t n, const float* d_queries, int64_t nq, float* D, int64_t ldd,
-                        uint64_t* launches);
+                        uint64_t* launches, const TcFused* fused = nullptr);
 
 // All-pairs variant used by the graph build: for queries = rows [q_start, q_start+nq) of the table.
 int brute_force_knn_rows(Index* ix, int64_t q_start, int64_t nq, int64_t n_rows, int64_t k,

@@ -17,6 +17,7 @@
 // sort — returned ids/distances are those of the fp32 path ("TF32 MMA with fp32 re-score of
 // survivors").  Bound: tensor pipe / L2 operand traffic.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <cstdlib>
 
@@ -32,7 +33,7 @@ constexpr int kTcABytes = kTcBM * kTcBK * 4;   // 16 KB
 constexpr int kTcBBytes = kTcBN * kTcBK * 4;   // 32 KB
 constexpr int kTcStageBytes = kTcABytes + kTcBBytes;
 constexpr int kTcThreads = 192;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
-constexpr int kTcSmem = kTcStages * kTcStageBytes + 1024 /*align*/ + 4096 /*qnorm*/ + 256 /*barriers*/;
+constexpr int kTcSmem = kTcStages * kTcStageBytes + 1024 /*align*/ + 8192 /*qnorm + thresholds*/ + 256 /*barriers*/;
 
 struct TcArgs {
   int64_t row_start;   // absolute first row of this chunk
@@ -46,6 +47,15 @@ struct TcArgs {
   int metric;
   int n_row_tiles;
   int n_q_tiles;
+  int kb_elems;        // elements per 128-byte k-block: 32 (fp32 read as TF32) or 64 (bf16 mirror)
+  uint32_t idesc;      // UMMA instruction descriptor for the operand type
+  // fused selection (D == nullptr): only entries below the query's running threshold leave the SM
+  const float* thr;             // [nq] coarse k'-th best so far
+  unsigned long long* cand;     // [nq x cand_cap] keys
+  int* cand_cnt;                // [nq]
+  const uint32_t* pass;         // deleted / static-filter bitmap relative to pass_base (may be null)
+  int64_t pass_base;
+  int cand_cap;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -89,16 +99,27 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return d;
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256 (InstrDescriptor bit layout, same header).
-__device__ __forceinline__ uint32_t umma_idesc_tf32() {
+__host__ __device__ __forceinline__ uint32_t umma_idesc(uint32_t fmt /* 2 = TF32, 1 = BF16 */) {
   uint32_t d = 0;
   d |= 1u << 4;                      // c_format = F32
-  d |= 2u << 7;                      // a_format = TF32
-  d |= 2u << 10;                     // b_format = TF32
+  d |= fmt << 7;                     // a_format
+  d |= fmt << 10;                    // b_format
   d |= (kTcBN >> 3) << 17;           // n_dim
   d |= (kTcBM >> 4) << 24;           // m_dim
   return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+template <bool BF16>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (BF16) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+    return;
+  }
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -117,14 +138,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
   // 1024-byte alignment for the 128-byte swizzle pattern
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   float* qn_s = reinterpret_cast<float*>(base + kTcStages * kTcStageBytes);  // [<=1024]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kTcStages * kTcStageBytes + 4096);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kTcStages * kTcStageBytes + 8192);
   // bars[0..3] full, [4..7] empty, [8..9] tmem_full, [10..11] tmem_empty, then the TMEM base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 4), tfull0 = smem_u32(bars + 8), tempty0 = smem_u32(bars + 10);
   const uint32_t stage0 = smem_u32(base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (a.dim + kTcBK - 1) / kTcBK;
+  const int nkb = (a.dim + a.kb_elems - 1) / a.kb_elems;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -135,8 +156,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (a.metric == EPS_METRIC_L2)
-    for (int i = threadIdx.x; i < a.nq && i < 1024; i += blockDim.x) qn_s[i] = a.qnorm[i];
+  float* thr_s = qn_s + 1024;  // [<=1024] thresholds (fused mode)
+  // fused mode compares t = m*dot + xn (m = -2 for L2, -1 otherwise) with a per-query constant:
+  //   L2: d = t + |q|^2 < thr  <=>  t < thr - |q|^2;   cosine: d = 1 + t < thr  <=>  t < thr - 1;   IP: d = t < thr.
+  // Queries beyond nq get -inf, so they never pass and need no bounds test in the inner loop.
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const float qn = (a.metric == EPS_METRIC_L2 && i < a.nq) ? a.qnorm[i] : 0.f;
+    qn_s[i] = qn;
+    float c = -INFINITY;
+    if (a.D == nullptr && i < a.nq) {
+      const float th = a.thr[i];
+      c = a.metric == EPS_METRIC_L2 ? th - qn : (a.metric == EPS_METRIC_COSINE ? th - 1.0f : th);
+    }
+    thr_s[i] = c;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -157,8 +190,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
             mbar_wait(empty0 + 8 * s, ph ^ 1);
             mbar_expect_tx(full0 + 8 * s, kTcStageBytes);
             const uint32_t sa = stage0 + s * kTcStageBytes;
-            tma_load_2d(sa, &tmA, kb * kTcBK, row0, full0 + 8 * s);
-            tma_load_2d(sa + kTcABytes, &tmB, kb * kTcBK, qt * kTcBN, full0 + 8 * s);
+            tma_load_2d(sa, &tmA, kb * a.kb_elems, row0, full0 + 8 * s);
+            tma_load_2d(sa + kTcABytes, &tmB, kb * a.kb_elems, qt * kTcBN, full0 + 8 * s);
           }
         }
       }
@@ -166,7 +199,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32();
+      const bool bf16 = a.kb_elems == 64;
+      const uint32_t idesc = bf16 ? umma_idesc(1u) : umma_idesc(2u);
       uint32_t it = 0, tc = 0;
       for (int rt = blockIdx.x; rt < a.n_row_tiles; rt += gridDim.x) {
         for (int qt = 0; qt < tiles_per_row; ++qt, ++tc) {
@@ -181,8 +215,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
             const uint32_t sa = stage0 + s * kTcStageBytes;
             const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + kTcABytes);
 #pragma unroll
-            for (int k = 0; k < kTcBK / 8; ++k)  // 4 x (K = 8 floats = 32 bytes = +2 in 16-byte units)
-              umma_tf32(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {  // 4 MMAs per 128-byte block: K = 8 tf32 / 16 bf16 = 32 bytes = +2 (16-B units)
+              if (bf16) umma_issue<true>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              else umma_issue<false>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            }
             umma_commit(empty0 + 8 * s);  // frees the stage when these MMAs retire
           }
           umma_commit(tfull0 + 8 * acc);  // accumulator complete
@@ -195,9 +231,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
     uint32_t tc = 0;
     for (int rt = blockIdx.x; rt < a.n_row_tiles; rt += gridDim.x) {
       const int64_t i = static_cast<int64_t>(rt) * kTcBM + lq + lane;  // row index inside the chunk
-      const bool row_ok = i < a.n;
+      bool row_ok = i < a.n;
       float xn = 0.f;
       if (a.metric == EPS_METRIC_L2 && row_ok) xn = a.xnorm[a.row_start + i];
+      const int64_t row_abs = a.row_start + i;
+      if (a.D == nullptr && a.pass && row_ok) {
+        const int64_t pi = row_abs - a.pass_base;
+        row_ok = (a.pass[pi >> 5] >> (pi & 31)) & 1u;
+      }
       for (int qt = 0; qt < tiles_per_row; ++qt, ++tc) {
         const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
         mbar_wait(tfull0 + 8 * acc, aph);
@@ -217,16 +258,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
               : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const int q0 = qt * kTcBN + c * 32;
+          if (a.D == nullptr) {
+            // ---- fused selection: 2 instructions per element (FFMA + compare), survivors are rare ----
+            if (row_ok) {
+              const float m = a.metric == EPS_METRIC_L2 ? -2.0f : -1.0f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int q = q0 + j;
-            if (row_ok && q < a.nq) {
-              const float dot = __uint_as_float(v[j]);
-              float d;
-              if (a.metric == EPS_METRIC_L2) d = fmaxf(xn + qn_s[q] - 2.0f * dot, 0.f);
-              else if (a.metric == EPS_METRIC_COSINE) d = 1.0f - dot;
-              else d = -dot;
-              a.D[static_cast<int64_t>(q) * a.ldd + i] = d;
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 ct = *reinterpret_cast<const float4*>(thr_s + q0 + 4 * j4);
+                const float t0 = fmaf(m, __uint_as_float(v[4 * j4 + 0]), xn), t1 = fmaf(m, __uint_as_float(v[4 * j4 + 1]), xn);
+                const float t2 = fmaf(m, __uint_as_float(v[4 * j4 + 2]), xn), t3 = fmaf(m, __uint_as_float(v[4 * j4 + 3]), xn);
+                if ((t0 < ct.x) | (t1 < ct.y) | (t2 < ct.z) | (t3 < ct.w)) {
+                  const float tt[4] = {t0, t1, t2, t3};
+                  const float cc[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    if (tt[u] < cc[u]) {
+                      const int q = q0 + 4 * j4 + u;
+                      float d = tt[u];
+                      if (a.metric == EPS_METRIC_L2) d = fmaxf(d + qn_s[q], 0.f);
+                      else if (a.metric == EPS_METRIC_COSINE) d = 1.0f + d;
+                      const int slot = atomicAdd(&a.cand_cnt[q], 1);
+                      if (slot < a.cand_cap) a.cand[static_cast<int64_t>(q) * a.cand_cap + slot] = make_key(d, static_cast<uint32_t>(row_abs));
+                    }
+                  }
+                }
+              }
+            }
+          } else {
+            // ---- distance tile to global memory (first chunk: seeds the running thresholds) ----
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int q = q0 + j;
+              if (row_ok && q < a.nq) {
+                const float dot = __uint_as_float(v[j]);
+                float d;
+                if (a.metric == EPS_METRIC_L2) d = fmaxf(xn + qn_s[q] - 2.0f * dot, 0.f);
+                else if (a.metric == EPS_METRIC_COSINE) d = 1.0f - dot;
+                else d = -dot;
+                a.D[static_cast<int64_t>(q) * a.ldd + i] = d;
+              }
             }
           }
         }
@@ -272,32 +342,53 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* tm, const float* base, int64_t rows, int dim, int box_rows) {
+static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int dim, int box_rows, bool bf16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(EPS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const int esz = bf16 ? 2 : 4;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 4};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kTcBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};  // 128-byte rows
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                   gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(EPS_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
   return EPS_OK;
 }
 
+__global__ void to_bf16_kernel(const float* __restrict__ in, int64_t n, unsigned short* __restrict__ out) {
+  const int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a);
+    o.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  } else {
+    for (int64_t j = i; j < n; ++j) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(in[j]);
+      out[j] = *reinterpret_cast<const unsigned short*>(&h);
+    }
+  }
+}
+
 bool tc_dist_usable(const Index* ix, int64_t nq) {
-  if (getenv("EPS_NO_TC")) return false;
-  if (nq < 64 || nq > 1024) return false;            // query norms live in a 4 KB shared-memory table
-  if (ix->dim % 4 != 0 || ix->dim < 32) return false;  // TMA: 16-byte row pitch
+  if (getenv("EPS_NO_TC") || ix->coarse_mode == 0) return false;
+  if (nq < 64 || nq > 1024) return false;            // per-query constants live in a 4 KB shared-memory table
+  const int align = ix->coarse_mode == 2 ? 8 : 4;    // TMA: 16-byte row pitch
+  if (ix->dim % align != 0 || ix->dim < 32) return false;
   if ((reinterpret_cast<uintptr_t>(ix->d_vectors) & 15) != 0) return false;
   return get_encode() != nullptr;
 }
 
-// Same contract as launch_distances() (D[q*ldd + i] for rows [row_start, row_start+n)), coarse TF32 values.
+// Same contract as launch_distances() (D[q*ldd + i] for rows [row_start, row_start+n)), coarse values; with
+// `fused` the tile is filtered against the running thresholds in the epilogue instead of being written.
 int tc_launch_distances(Index* ix, int64_t row_start, int64_t n, const float* d_queries, int64_t nq, float* D,
-                        int64_t ldd, uint64_t* launches) {
+                        int64_t ldd, uint64_t* launches, const TcFused* fused) {
   const int dim = static_cast<int>(ix->dim);
+  const bool bf16 = ix->coarse_mode == 2;
   if (ix->metric == EPS_METRIC_L2) {
     if (ix->xnorm_rows < ix->n_rows) {  // row norms for rows appended since the last call
       EPS_TRY(ix->s_xnorm.reserve(static_cast<size_t>(ix->capacity > ix->n_rows ? ix->capacity : ix->n_rows) * 4));
@@ -313,12 +404,40 @@ int tc_launch_distances(Index* ix, int64_t row_start, int64_t n, const float* d_
                                                                                          ix->s_qnorm.as<float>());
     ++*launches;
   }
+  const void* a_base = ix->d_vectors;
+  const void* b_base = d_queries;
+  if (bf16) {
+    // bf16 mirror of the table (coarse pass only; the re-score reads the fp32 rows), kept current incrementally
+    if (ix->bf16_rows < ix->n_rows) {
+      EPS_TRY(ix->s_bf16.reserve(static_cast<size_t>(ix->capacity > ix->n_rows ? ix->capacity : ix->n_rows) * dim * 2));
+      if (ix->s_bf16.p != ix->bf16_ptr) { ix->bf16_rows = 0; ix->bf16_ptr = ix->s_bf16.p; }
+      const int64_t cnt = (ix->n_rows - ix->bf16_rows) * dim;
+      to_bf16_kernel<<<static_cast<unsigned>((cnt / 4 + 256) / 256), 256, 0, ix->stream>>>(
+          ix->d_vectors + ix->bf16_rows * dim, cnt, ix->s_bf16.as<unsigned short>() + ix->bf16_rows * dim);
+      ix->bf16_rows = ix->n_rows;
+      ++*launches;
+    }
+    EPS_TRY(ix->s_qbf16.reserve(static_cast<size_t>(nq) * dim * 2));
+    const int64_t cnt = nq * dim;
+    to_bf16_kernel<<<static_cast<unsigned>((cnt / 4 + 256) / 256), 256, 0, ix->stream>>>(d_queries, cnt, ix->s_qbf16.as<unsigned short>());
+    ++*launches;
+    a_base = ix->s_bf16.p;
+    b_base = ix->s_qbf16.p;
+  }
   CUtensorMap tmA, tmB;
-  EPS_TRY(make_map(&tmA, ix->d_vectors, ix->n_rows, dim, kTcBM));
-  EPS_TRY(make_map(&tmB, d_queries, nq, dim, kTcBN));
+  EPS_TRY(make_map(&tmA, a_base, ix->n_rows, dim, kTcBM, bf16));
+  EPS_TRY(make_map(&tmB, b_base, nq, dim, kTcBN, bf16));
   TcArgs a;
   a.row_start = row_start; a.n = n; a.nq = nq; a.ldd = ldd;
   a.xnorm = ix->s_xnorm.as<float>(); a.qnorm = ix->s_qnorm.as<float>(); a.D = D; a.dim = dim; a.metric = ix->metric;
+  a.kb_elems = bf16 ? 64 : 32;
+  a.idesc = umma_idesc(bf16 ? 1u : 2u);
+  a.thr = nullptr; a.cand = nullptr; a.cand_cnt = nullptr; a.pass = nullptr; a.pass_base = 0; a.cand_cap = 0;
+  if (fused) {
+    a.D = nullptr;
+    a.thr = fused->thr; a.cand = fused->cand; a.cand_cnt = fused->cand_cnt; a.pass = fused->pass;
+    a.pass_base = fused->pass_base; a.cand_cap = fused->cand_cap;
+  }
   a.n_row_tiles = static_cast<int>((n + kTcBM - 1) / kTcBM);
   a.n_q_tiles = static_cast<int>((nq + kTcBN - 1) / kTcBN);
   EPS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));

@@ -103,6 +103,10 @@ class Index:
         L_local = L_master if L_local is None else L_local
         check(self.L.eps_index_config(self.h, int(L_master), int(L_local), int(bool(prefilter)), int(bool(force_brute))))
 
+    def set_coarse(self, mode):
+        """0 = fp32 SIMT only, 1 = tcgen05 TF32 (default), 2 = tcgen05 bf16 mirror (exact re-score in all modes)."""
+        check(self.L.eps_index_set_coarse(self.h, {"fp32": 0, "tf32": 1, "bf16": 2}.get(mode, mode)))
+
     # --- search ---
     def search(self, queries, limit, filter_nodes=None, want_stats=True):
         """HOST buffers in/out (eps_search_batch).  Returns ids [nq,limit], dists float64, counts, Stats."""
