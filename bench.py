@@ -52,7 +52,7 @@ def parse():
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--metric", default="l2")
     p.add_argument("--dist", default="uniform", choices=["uniform", "cluster"])
-    p.add_argument("--modes", default="graph,brute", help="candidate modes: graph,brute")
+    p.add_argument("--modes", default="graph,brute-bf16,brute-tf32", help="candidate modes: graph, brute-bf16, brute-tf32, brute-fp32")
     p.add_argument("--L-sweep", default="512,2048", help="graph queue lengths to try")
     p.add_argument("--graph-rows-max", type=int, default=int(os.environ.get("EPS_BENCH_GRAPH_ROWS_MAX", "0")),
                    help="build/search the graph only when rows <= this (0 = graph mode off)")
@@ -285,6 +285,7 @@ def main():
 
     # ---- exact ground truth for recall (the exact-scan mode itself; cross-checked in fp64 on a sample) ----
     ix.config(512, 512, force_brute=True)
+    ix.set_coarse("fp32")  # ground truth = the fp32 SIMT exact scan (no tensor-core coarse pass), fp64-checked below
     Qt = Qpool[0]
     ix.search_device(Qt.data_ptr(), a.batch, a.k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr())
     truth = out_ids.clone()
@@ -324,15 +325,19 @@ def main():
         torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
         for L in [int(x) for x in a.L_sweep.split(",")]:
-            modes.append(("graph", L))
-    if "brute" in want or not modes:
-        modes.append(("brute", 0))
+            modes.append(("graph", L, ""))
+    for w in want:
+        if w.startswith("brute"):
+            modes.append(("brute", 0, w.split("-")[1] if "-" in w else "tf32"))
+    if not modes:
+        modes.append(("brute", 0, "tf32"))
 
     def set_mode(m):
         if m[0] == "graph":
             ix.config(m[1], m[1], force_brute=False)
         else:
             ix.config(512, 512, force_brute=True)
+            ix.set_coarse(m[2])
 
     def timed_device_steps(m, n_steps, first):
         """Device-resident inputs: CUDA events on the launch stream; max over ranks."""
@@ -358,15 +363,15 @@ def main():
     for m in modes:
         set_mode(m)
         ix.search_device(Qt.data_ptr(), a.batch, a.k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr())
-        rec = recall_of(out_ids) if m[0] == "graph" else 1.0  # the exact scan IS the ground truth (fp64-checked above)
+        rec = recall_of(out_ids)
         timed_device_steps(m, a.warmup, 0)
         ms, stats = timed_device_steps(m, max(2, min(a.steps, 3)), a.warmup)
         qps = world * a.batch * len(stats) / (ms / 1000.0) if not a.shard_rows else a.batch * len(stats) / (ms / 1000.0)
-        report.append({"mode": m[0], "L": m[1], "recall_at_%d" % a.k: rec, "qps_probe": qps,
+        report.append({"mode": m[0], "L": m[1], "coarse": m[2], "recall_at_%d" % a.k: rec, "qps_probe": qps,
                        "n_dist_per_query": float(np.mean([s["n_dist"] for s in stats])) / a.batch})
     ok = [r for r in report if r["recall_at_%d" % a.k] >= a.recall_target]
     chosen = max(ok, key=lambda r: r["qps_probe"]) if ok else max(report, key=lambda r: r["recall_at_%d" % a.k])
-    mode = (chosen["mode"], chosen["L"])
+    mode = (chosen["mode"], chosen["L"], chosen["coarse"])
 
     # ---- timed region: `value` (inputs resident in HBM) ----
     clocks = ClockSampler(local)
@@ -443,15 +448,16 @@ def main():
         bytes_alg = (n_dist - n_seed) * a.dim * 4.0 + n_edges * deg_bytes + n_exp * 16.0 + \
             a.steps * (mode[1] * a.dim * 4.0) + a.steps * a.batch * (a.dim * 4.0 + a.k * 12.0)
         kernel_name = "graph_search_kernel"
-    if mode[0] == "brute" and not os.environ.get("EPS_NO_TC"):
+    if mode[0] == "brute" and mode[2] != "fp32" and not os.environ.get("EPS_NO_TC"):
         # exact scan at B=1024 is a dense contraction (512 flop/B): tcgen05 kind::tf32 coarse pass + fp32 re-score.
         # Roofline = tensor pipe.  TF32 runs at half the bf16 rate on tcgen05, so peak = measured bf16 / 2.
         flop = a.steps * rows * float(a.batch) * a.dim * 2.0
         ach = flop / (kernel_ms / 1000.0) / 1e12 if kernel_ms > 0 else 0.0
-        peak = tf_peak / 2.0
+        peak = tf_peak / 2.0 if mode[2] == "tf32" else tf_peak
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "kernel": "tc_dist_kernel (tcgen05 kind::tf32) + bf_select_kernel + rescore_kernel",
-                "peak_source": "%s bf16 sustained (%.0f TF/s) / 2 for TF32" % (peak_src, tf_peak),
+                "kernel": "tc_dist_kernel (tcgen05 kind::%s, fused threshold select) + bf_select_kernel + rescore_kernel" % (
+                    "tf32" if mode[2] == "tf32" else "f16/bf16"),
+                "peak_source": "%s bf16 sustained (%.0f TF/s)%s" % (peak_src, tf_peak, " / 2 for TF32" if mode[2] == "tf32" else ""),
                 "kernel_ms_per_step": kernel_ms / a.steps,
                 "hbm_algorithmic_GBps": bytes_alg / (kernel_ms / 1000.0) / 1e9 if kernel_ms > 0 else 0.0}
     else:
@@ -467,7 +473,7 @@ def main():
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%dx%d f32 %s iid-%s (seed 42), batch=%d, top-%d, mode=%s%s; %s" % (
-            rows, a.dim, a.metric, a.dist, a.batch, a.k, mode[0], (" L=%d" % mode[1]) if mode[0] == "graph" else "",
+            rows, a.dim, a.metric, a.dist, a.batch, a.k, mode[0], (" L=%d" % mode[1]) if mode[0] == "graph" else " (exact scan: tcgen05 %s coarse pass + fp32 re-score)" % mode[2],
             "row shards + NCCL all-gather" if a.shard_rows else "replicated table, query stream partitioned over ranks"),
             "recall_at_%d" % a.k: chosen["recall_at_%d" % a.k], "l2_flush": "inputs (%.1f GB table) larger than L2" % (
                 rows * a.dim * 4 / 1e9), "fp64_groundtruth_check": chk},

@@ -258,3 +258,58 @@ def test_device_api_and_shard_merge(vdb):
     assert torch.all(out_d[:, 1:] >= out_d[:, :-1])
     for ix in keep:
         ix.close()
+
+
+# ---- exact scan on the tensor cores: coarse tcgen05 pass (tf32 / bf16 mirror) + fp32 re-score -------------------
+def test_exact_scan_coarse_modes_match_oracle(vdb, port):
+    n, d, nq, k = 60000, 96, 128, 10
+    X, Q = gen(n, d, 301), gen(nq, d, 302)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.config(500, 500, force_brute=True)
+    pids, pds, pcnt, _ = port.search_batch(metric="l2", vectors=X, queries=Q[:8], limit=k, L=500, prefilter=True)
+    res = {}
+    for mode in ("fp32", "tf32", "bf16"):
+        ix.set_coarse(mode)
+        ids, ds, cnt, st = ix.search(Q, k)
+        assert_same_results(ids[:8], ds[:8], cnt[:8], pids, pds, pcnt, "coarse=" + mode)
+        assert np.all(np.diff(ds, axis=1) >= 0)
+        res[mode] = ids
+    # re-scored results carry fp32-exact distances, so the three modes agree up to equal-distance swaps
+    assert (res["tf32"] == res["fp32"]).mean() > 0.999 and (res["bf16"] == res["fp32"]).mean() > 0.999
+    # deleted rows and a distance-free filter go through the pass bitmap inside the fused epilogue
+    bits = np.zeros((n + 7) // 8, np.uint8)
+    dead = res["fp32"][:, 0]
+    for i in dead:
+        bits[i >> 3] |= 1 << (i & 7)
+    ix.set_deleted(bits)
+    for mode in ("fp32", "bf16"):
+        ix.set_coarse(mode)
+        ids, ds, cnt, _ = ix.search(Q, k)
+        assert not (set(ids.ravel().tolist()) & set(dead.tolist()))
+        res["del_" + mode] = ids
+    assert (res["del_bf16"] == res["del_fp32"]).mean() > 0.999
+    ix.close()
+
+
+def test_exact_scan_adversarial_row_order_falls_back(vdb):
+    """Rows ordered so that EVERY later row beats the running thresholds: the fused candidate buffers overflow,
+    which must be detected and answered by the fp32 path — never by dropping candidates."""
+    n, d, nq, k = 200000, 32, 64, 10
+    rng = np.random.default_rng(5)
+    U = rng.standard_normal((n, d)).astype(np.float32)
+    U /= np.linalg.norm(U, axis=1, keepdims=True)
+    scale = np.linspace(8.0, 1.0, n, dtype=np.float32)[:, None]  # later rows are closer to the origin
+    X = (U * scale).astype(np.float32)
+    Q = (0.01 * rng.standard_normal((nq, d))).astype(np.float32)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.config(500, 500, force_brute=True)
+    ix.set_coarse("fp32")
+    want, wd, _, _ = ix.search(Q, k)
+    ix.set_coarse("bf16")
+    got, gd, _, _ = ix.search(Q, k)
+    assert np.allclose(gd, wd, rtol=1e-5)
+    assert (got == want).mean() > 0.99
+    assert got.min() >= n - 5000  # the answers are the last rows
+    ix.close()
