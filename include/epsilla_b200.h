@@ -136,6 +136,12 @@ EPS_API int eps_index_set_attrs(eps_index* ix, const char* attribute_table, int6
  * search an exact scan (what the reference does for un-indexed tables). */
 EPS_API int eps_index_config(eps_index* ix, int64_t L_master, int64_t L_local, int prefilter, int force_brute);
 
+/* Graph-search expansion width: how many unchecked queue entries are expanded per iteration.  1 (default)
+ * reproduces the reference at IntraQueryThreads = 1 exactly; 2 / 4 are the device analogue of the reference's
+ * IntraQueryThreads > 1 (config.hpp:18, default 4): candidates expanded in parallel against a slightly stale
+ * bound — higher throughput, results not bit-identical to the sequential order (as in the reference). */
+EPS_API int eps_index_set_search_width(eps_index* ix, int width);
+
 /* Precision of the COARSE pass of large-batch exact scans (nq >= 64): 0 = none (fp32 SIMT tiles only),
  * 1 = tcgen05 kind::tf32 on the fp32 rows (default), 2 = tcgen05 kind::f16 on a bf16 mirror of the table
  * (+50 % HBM).  Whatever the mode, the k + max(32, k) best coarse candidates of every query are re-evaluated

@@ -313,3 +313,28 @@ def test_exact_scan_adversarial_row_order_falls_back(vdb):
     assert (got == want).mean() > 0.99
     assert got.min() >= n - 5000  # the answers are the last rows
     ix.close()
+
+
+def test_wide_expansion_matches_sequential_quality(vdb, port):
+    """expand width 2/4 = the analogue of the reference's IntraQueryThreads > 1: not bit-identical to the
+    sequential order, but the same answers on (almost) every query — like the reference's own T=4 vs T=1."""
+    n, d, nq = 20000, 64, 64
+    X, Q = gen(n, d, 401, "cluster"), gen(nq, d, 402, "cluster")
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.build(n)
+    ix.config(256, 256)
+    truth = exact_topk(X, Q, 10)
+    base, bd, _, st1 = ix.search(Q, 10)
+    r1 = recall(base, truth, 10)
+    for w in (2, 4):
+        ix.set_search_width(w)
+        ids, ds, cnt, st = ix.search(Q, 10)
+        assert np.all(cnt == 10) and np.all(np.diff(ds, axis=1) >= 0)
+        assert recall(ids, truth, 10) >= r1 - 0.01
+        assert (ids == base).mean() > 0.97
+        assert st["n_dist"] <= 1.3 * st1["n_dist"]
+    ix.set_search_width(1)
+    again, _, _, _ = ix.search(Q, 10)
+    assert np.array_equal(again, base)
+    ix.close()

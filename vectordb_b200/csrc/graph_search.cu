@@ -403,6 +403,181 @@ __global__ void __launch_bounds__(128, 7) graph_search_kernel_v2(GS2Args a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Wide variant: W unchecked candidates are expanded per iteration (their neighbour rows are tested, gathered
+// and merged together).  This is the device analogue of the reference's IntraQueryThreads > 1 mode
+// (vec_search_executor.cpp:601-698: M candidates dealt to workers, expanded against a slightly stale bound,
+// merged back) — like that mode it is NOT bit-identical to the sequential order (W = 1, kernels above, is);
+// it trades that for W-fold fewer dependent round trips per query.  Same queue / visited / bound rules.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWideMax = 4;
+constexpr int kWCap = kWideMax * kEll;  // fresh / candidate slots per iteration
+
+__global__ void __launch_bounds__(128, 7) graph_search_kernel_wide(GS2Args a, int W) {
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  unsigned long long* qa = reinterpret_cast<unsigned long long*>(gs_smem);  // [Lp]
+  unsigned long long* cand = qa + a.Lp;                                     // [kWCap]
+  unsigned long long* cs = cand + kWCap;                                    // [kWCap]
+  float* qv = reinterpret_cast<float*>(cs + kWCap);                         // [dim4]
+  int* pos = reinterpret_cast<int*>(qv + ((a.dim + 3) & ~3));               // [kWCap]
+  int* fresh = pos + kWCap;                                                 // [kWCap]
+  __shared__ int s_q, s_ncur, s_first, s_nfresh, s_nacc, s_pmin, s_more;
+  __shared__ int s_cid[kWideMax];
+  __shared__ unsigned long long s_ndist, s_nexp, s_nedge;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint32_t* visited = a.visited + static_cast<int64_t>(blockIdx.x) * a.visited_words;
+  const int L = a.L;
+  if (tid == 0) { s_ndist = 0; s_nexp = 0; s_nedge = 0; }
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_q = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int q = s_q;
+    if (q >= a.nq) break;
+    for (int i = tid; i < a.dim; i += blockDim.x) qv[i] = a.queries[static_cast<int64_t>(q) * a.dim + i];
+    for (int i = tid; i < a.Lp; i += blockDim.x) {
+      unsigned long long key = kKeyInf;
+      if (i < L) {
+        const uint32_t id = static_cast<uint32_t>(a.init_ids[i]);
+        atomicOr(&visited[id >> 5], 1u << (id & 31));
+        key = make_key(a.seed_dist[static_cast<int64_t>(q) * a.seed_ld + i], id);
+      }
+      qa[i] = key;
+    }
+    if (tid == 0) { s_nfresh = 0; s_nacc = 0; }
+    __syncthreads();
+    block_bitonic_sort(qa, a.Lp);
+
+    int k = 0;
+    for (;;) {
+      if (warp == 0) {
+        int cnt = 0, first = -1;
+        for (int p = k; p < L && cnt < W; p += 32) {
+          const int idx = p + lane;
+          const bool un = idx < L && !(qa[idx] & kCheckedBit);
+          unsigned b = __ballot_sync(kFull, un);
+          while (b && cnt < W) {
+            const int at = p + __ffs(b) - 1;
+            if (first < 0) first = at;
+            if (lane == 0) { s_cid[cnt] = static_cast<int>(key_id(qa[at])); qa[at] |= kCheckedBit; }
+            b &= b - 1;
+            ++cnt;
+          }
+        }
+        if (lane == 0) { s_ncur = cnt; s_first = first; s_pmin = L; s_more = 0; }
+      }
+      __syncthreads();  // (1)
+      const int ncur = s_ncur;
+      if (ncur == 0) break;
+      for (int slot = tid; slot < ncur * kEll; slot += blockDim.x) {
+        const int ci = slot / kEll, e = slot % kEll;
+        const int nb = __ldg(a.ell + static_cast<int64_t>(s_cid[ci]) * kEll + e);
+        if (nb >= 0) {
+          const uint32_t bit = 1u << (nb & 31);
+          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
+          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = nb;
+          if (e == kEll - 1) atomicOr(&s_more, 1 << ci);
+        }
+      }
+      __syncthreads();  // (2)
+      if (tid == 0) s_nexp += static_cast<unsigned long long>(ncur);
+      const int more = s_more;
+      int over_ci = -1;  // candidate whose CSR continuation is being drained (rare: rows longer than kEll)
+      int64_t e_next = 0, e_end = 0;
+      for (;;) {
+        const int nfresh = s_nfresh;
+        const unsigned long long bound = qa[L - 1] & kKeyMask;
+        for (int i = warp; i < nfresh; i += nwarps) {
+          const int nb = fresh[i];
+          float d = warp_distance(a.metric, a.vec4 != 0, a.vectors + static_cast<int64_t>(nb) * a.dim, qv, a.dim, lane);
+          if (lane == 0) {
+            const unsigned long long key = make_key(d, static_cast<uint32_t>(nb));
+            if (key < bound) cand[atomicAdd(&s_nacc, 1)] = key;
+          }
+        }
+        __syncthreads();  // (3)
+        const int m = s_nacc;
+        if (m > 0) {
+          for (int i = tid; i < m; i += blockDim.x) {
+            const unsigned long long key = cand[i];
+            int r = 0;
+            for (int j = 0; j < m; ++j) r += (cand[j] < key);
+            cs[r] = key;
+          }
+          __syncthreads();
+          for (int i = tid; i < m; i += blockDim.x) pos[i] = lb_masked(qa, L, cs[i]);
+          __syncthreads();
+          const int p0 = pos[0];
+          for (int hi = L; hi > p0; hi -= 8 * 128) {
+            unsigned long long kreg[8];
+            int dreg[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = hi - 1 - (u * 128 + tid);
+              dreg[u] = L;
+              if (j >= p0) {
+                kreg[u] = qa[j];
+                int sft = 0;
+                if (m <= 8) { for (int i = 0; i < m; ++i) sft += (pos[i] <= j); }
+                else { int lo = 0, up = m; while (lo < up) { const int mid = (lo + up) >> 1; if (pos[mid] <= j) lo = mid + 1; else up = mid; } sft = lo; }
+                dreg[u] = j + sft;
+              }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (dreg[u] < L) qa[dreg[u]] = kreg[u];
+            __syncthreads();
+          }
+          for (int i = tid; i < m; i += blockDim.x) {
+            const int f = pos[i] + i;
+            if (f < L) qa[f] = cs[i];
+          }
+          if (tid == 0 && p0 < s_pmin) s_pmin = p0;
+        }
+        if (tid == 0) { s_ndist += static_cast<unsigned long long>(nfresh); s_nfresh = 0; s_nacc = 0; }
+        __syncthreads();
+        // next CSR continuation chunk, if any candidate's row exceeded the fixed stride
+        while (e_next >= e_end) {
+          ++over_ci;
+          while (over_ci < ncur && !((more >> over_ci) & 1)) ++over_ci;
+          if (over_ci >= ncur) break;
+          e_next = a.offsets[s_cid[over_ci]] + kEll;
+          e_end = a.offsets[s_cid[over_ci] + 1];
+        }
+        if (over_ci >= ncur) break;
+        const int cnt = static_cast<int>(min(static_cast<int64_t>(kEll), e_end - e_next));
+        if (tid < cnt) {
+          const uint32_t nb = static_cast<uint32_t>(a.nbrs[e_next + tid]);
+          const uint32_t bit = 1u << (nb & 31);
+          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
+          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = static_cast<int>(nb);
+        }
+        e_next += cnt;
+        __syncthreads();
+      }
+      const int pmin = s_pmin, first = s_first;
+      k = pmin < first + 1 ? pmin : first + 1;
+    }
+
+    unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
+    for (int i = tid; i < L; i += blockDim.x) out[i] = qa[i];
+    {
+      uint4* v4 = reinterpret_cast<uint4*>(visited);
+      const int64_t n4 = a.visited_words >> 2;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int64_t i = tid; i < n4; i += blockDim.x) v4[i] = z;
+    }
+    if (tid == 0) s_ndist += static_cast<unsigned long long>(L);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(&a.stats[0], s_ndist);
+    atomicAdd(&a.stats[1], s_nexp);
+  }
+}
+
 __global__ void csr_to_ell_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbrs, int64_t n,
                                   int32_t* __restrict__ ell) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -468,11 +643,16 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   EPS_TRY(prepare_init_ids(ix, L));
   const int dimp = (static_cast<int>(ix->dim) + 3) & ~3;
   const bool use_v2 = getenv("EPS_GRAPH_V1") == nullptr;
-  const size_t smem = use_v2 ? static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4 + 2 * kEll * 4
+  const int width = use_v2 ? std::max(1, std::min(ix->search_width, kWideMax)) : 1;
+  const size_t smem = width > 1 ? static_cast<size_t>(Lp) * 8 + 2 * kWCap * 8 + static_cast<size_t>(dimp) * 4 + 2 * kWCap * 4
+                      : use_v2 ? static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4 + 2 * kEll * 4
                              : static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4;
   if (smem > 220 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query do not fit in shared memory");
   int per_sm = 0;
-  if (use_v2) {
+  if (width > 1) {
+    EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel_wide, 128, smem));
+  } else if (use_v2) {
     EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel_v2, 128, smem));
   } else {
@@ -523,7 +703,8 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
     a.stats = ix->s_misc.as<unsigned long long>();
     a.visited_words = words; a.seed_ld = seed_ld; a.dim = static_cast<int>(ix->dim); a.metric = ix->metric;
     a.vec4 = ix->vec4 ? 1 : 0; a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
-    graph_search_kernel_v2<<<slots, 128, smem, ix->stream>>>(a);
+    if (width > 1) graph_search_kernel_wide<<<slots, 128, smem, ix->stream>>>(a, width);
+    else graph_search_kernel_v2<<<slots, 128, smem, ix->stream>>>(a);
   } else {
     GSArgs a;
     a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.init_ids = ix->d_init_ids;

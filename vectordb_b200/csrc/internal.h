@@ -54,6 +54,7 @@ struct Index {
   int64_t L_master = 500, L_local = 500;
   bool prefilter = false;
   bool force_brute = false;
+  int search_width = 1;          // candidates expanded per iteration (1 = the reference's sequential order)
 
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -103,6 +103,10 @@ class Index:
         L_local = L_master if L_local is None else L_local
         check(self.L.eps_index_config(self.h, int(L_master), int(L_local), int(bool(prefilter)), int(bool(force_brute))))
 
+    def set_search_width(self, width):
+        """1 = sequential expansion order of the reference (IntraQueryThreads=1); 2/4 = parallel expansion."""
+        check(self.L.eps_index_set_search_width(self.h, int(width)))
+
     def set_coarse(self, mode):
         """0 = fp32 SIMT only, 1 = tcgen05 TF32 (default), 2 = tcgen05 bf16 mirror (exact re-score in all modes)."""
         check(self.L.eps_index_set_coarse(self.h, {"fp32": 0, "tf32": 1, "bf16": 2}.get(mode, mode)))
