@@ -56,6 +56,7 @@ def parse():
     p.add_argument("--L-sweep", default="512,2048", help="graph queue lengths to try")
     p.add_argument("--graph-rows-max", type=int, default=int(os.environ.get("EPS_BENCH_GRAPH_ROWS_MAX", "0")),
                    help="build/search the graph only when rows <= this (0 = graph mode off)")
+    p.add_argument("--width", type=int, default=4, help="graph expansion width (1 = reference sequential order)")
     p.add_argument("--shard-rows", action="store_true")
     p.add_argument("--recall-target", type=float, default=0.99)
     p.add_argument("--cpu-queries", type=int, default=32)
@@ -321,7 +322,7 @@ def main():
     build_s = None
     if graph_ok:
         t0 = time.perf_counter()
-        ix.build(rows)
+        ix.build(rows, knn_k=64, nnd_iters=10)
         torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
         for L in [int(x) for x in a.L_sweep.split(",")]:
@@ -335,6 +336,7 @@ def main():
     def set_mode(m):
         if m[0] == "graph":
             ix.config(m[1], m[1], force_brute=False)
+            ix.set_search_width(a.width)
         else:
             ix.config(512, 512, force_brute=True)
             ix.set_coarse(m[2])

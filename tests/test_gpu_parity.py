@@ -338,3 +338,31 @@ def test_wide_expansion_matches_sequential_quality(vdb, port):
     again, _, _, _ = ix.search(Q, 10)
     assert np.array_equal(again, base)
     ix.close()
+
+
+def test_large_batch_top100_with_filter(vdb, port):
+    """Config C3 shape at test scale: batch > 1024 (grouped through the tensor-core pass), top-100, INT4 metadata
+    filter 'attr < 10' (10 % selectivity) evaluated on device, both as exact scan and as graph post-filter."""
+    n, d, nq, k = 50000, 64, 1536, 100
+    X, Q = gen(n, d, 501), gen(nq, d, 502)
+    attr = (np.arange(n) % 100).astype(np.int32)
+    nodes = np.array([[7, 1, -1, -1, 0, 0, 0, 0],      # Int4Attr at offset 0
+                      [1, 1, -1, -1, 10, 0, 0, -1],    # IntConst 10
+                      [19, 3, 0, 1, 0, 0, 0, -1]],     # LT
+                     np.int64)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.set_attrs(attr.view(np.uint8), 4, n)
+    ix.config(500, 500, force_brute=True)
+    ix.set_coarse("bf16")
+    ids, ds, cnt, _ = ix.search(Q, k, filter_nodes=nodes)
+    assert np.all(cnt == k) and np.all(attr[ids] < 10)
+    sub = [0, 700, 1100, 1535]
+    pids, pds, pcnt, _ = port.search_batch(metric="l2", vectors=X, queries=Q[sub], limit=k, L=500, prefilter=True,
+                                           attrs=attr.view(np.uint8), attr_stride=4, filter_nodes=nodes)
+    assert_same_results(ids[sub], ds[sub], cnt[sub], pids, pds, pcnt, "C3 exact scan + filter")
+    ix.config(500, 500, force_brute=False)
+    ix.build(n)
+    gids, gds, gcnt, _ = ix.search(Q[:64], k, filter_nodes=nodes)  # post-filter: only the best L are considered
+    assert np.all(gcnt <= k) and np.all(attr[gids[gids >= 0]] < 10)
+    ix.close()

@@ -597,6 +597,16 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
 int brute_force_topk(Index* ix, const float* d_queries, int64_t nq, int64_t row_start, int64_t row_end, int64_t k,
                      const FilterProg* d_prog, const FilterProg* h_prog, bool prefilter, unsigned long long* d_topk,
                      eps_stats* stats) {
+  // The tensor-core pass keeps its per-query constants in a 1024-entry shared-memory table: larger batches
+  // (config C3: B = 4096) go through it in groups of 1024 queries.
+  if (nq > 1024 && row_end - row_start >= 4096 && tc_dist_usable(ix, 1024)) {
+    for (int64_t q0 = 0; q0 < nq; q0 += 1024) {
+      const int64_t g = std::min<int64_t>(1024, nq - q0);
+      EPS_TRY(topk_impl(ix, d_queries + q0 * ix->dim, g, row_start, row_end, k, d_prog, h_prog, prefilter, -1, d_topk + q0 * k,
+                        stats));
+    }
+    return EPS_OK;
+  }
   return topk_impl(ix, d_queries, nq, row_start, row_end, k, d_prog, h_prog, prefilter, -1, d_topk, stats);
 }
 
