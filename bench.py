@@ -290,6 +290,7 @@ def main():
     Qt = Qpool[0]
     ix.search_device(Qt.data_ptr(), a.batch, a.k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr())
     truth = out_ids.clone()
+    truth_d = out_d.clone()
     chk = 0.0
     with torch.no_grad():
         qs = Qt[:4].double()
@@ -436,6 +437,14 @@ def main():
         x1.record()
         barrier()
         exchange_ms = x0.elapsed_time(x1) / a.steps
+        # correctness of the exchange: merged results of the last timed step's batch vs merged exact ground truth
+        set_mode(mode)
+        ix.search_device(Qt.data_ptr(), a.batch, a.k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr())
+        gi, gd = sharded.exchange_and_merge(out_ids, out_d, rank * rows, a.k, dist, merge_fn)
+        got = gi.cpu().numpy().copy()
+        ti, td = sharded.exchange_and_merge(truth, truth_d, rank * rows, a.k, dist, merge_fn)
+        want = ti.cpu().numpy()
+        merged_recall = float(np.mean([len(set(got[i].tolist()) & set(want[i].tolist())) / a.k for i in range(a.batch)]))
 
     units = a.batch * a.steps * (1 if a.shard_rows else world)
     value = units / ((ms_dev + (exchange_ms or 0.0) * a.steps) / 1000.0)
@@ -487,6 +496,7 @@ def main():
         out["graph_build_s"] = build_s
     if exchange_ms is not None:
         out["exchange_ms_per_step"] = exchange_ms
+        out["merged_recall_at_%d" % a.k] = merged_recall
 
     # ---- the reference's CPU path on this box's host cores (rank 0, N = 1 only) ----
     if rank == 0 and world == 1 and not a.no_cpu:
