@@ -17,15 +17,18 @@
 // NumExecutorPerField executors TableMVP creates for a field (engine/db/table_mvp.cpp:72-89) and destroyed
 // with the last of them — ownership rides on the executor's own ann_index_ shared_ptr (aliasing
 // constructor), so the reference's inline destructor needs no hook.  Calls on a mirror are serialised by a
-// mutex (an executor is not re-entrant in the reference either; coalescing concurrent single-query calls
-// into one batched launch is SURVEY.md §8f-2, next).
+// mutex; concurrent unfiltered single-query calls from the executors of a pool are COALESCED into one batched
+// launch by a leader/follower batch former — the reference API stays one query per call.
 //
 // Scope limits, reported as a non-OK Status instead of silently computing on the CPU: sparse-vector fields
 // and string / IN / LIKE / NEARBY filter nodes.
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "db/ann_graph_segment.hpp"
 #include "db/execution/vec_search_executor.hpp"
@@ -52,6 +55,21 @@ struct Mirror {
   int64_t nav = 0;
   int64_t* offsets = nullptr;
   int64_t* nbrs = nullptr;
+  // Coalescing of concurrent single-query calls: unfiltered searches that arrive while
+  // another executor's call is in flight are gathered and served by ONE batched launch.
+  struct Pending {
+    const float* query;
+    size_t limit;
+    int64_t* ids;
+    double* dists;
+    int64_t count = 0;
+    int rc = EPS_OK;
+    bool done = false;
+  };
+  std::mutex qmu;
+  std::condition_variable qcv;
+  std::vector<Pending*> waiting;
+  bool leader_active = false;
   ~Mirror() {
     if (ix) eps_index_destroy(ix);
   }
@@ -75,6 +93,58 @@ static int MetricOf(const DistFunc& f) {
 
 static Status Fail(const char* what) {
   return Status(DB_UNEXPECTED_ERROR, std::string("epsilla_b200: ") + what + ": " + eps_last_error());
+}
+
+// Leader/follower batch former.  The first caller becomes the leader: it waits a short window for followers,
+// then serves every queued request with the same limit in one eps_search_batch call (other limits in further
+// calls), copies each result out and wakes the followers.  Requests keep their per-call semantics (one query,
+// own result arrays); only the launch is shared.
+static int SearchCoalesced(Mirror* m, const float* query, size_t limit, int64_t* ids, double* dists, int64_t* count) {
+  Mirror::Pending me;
+  me.query = query; me.limit = limit; me.ids = ids; me.dists = dists;
+  std::unique_lock<std::mutex> q(m->qmu);
+  m->waiting.push_back(&me);
+  if (m->leader_active) {
+    m->qcv.wait(q, [&] { return me.done || !m->leader_active; });
+    if (me.done) { *count = me.count; return me.rc; }
+    // the leader left before taking this request: fall through and lead
+  }
+  m->leader_active = true;
+  while (!me.done) {
+    m->qcv.wait_for(q, std::chrono::microseconds(100));  // batching window
+    std::vector<Mirror::Pending*> batch;
+    std::vector<Mirror::Pending*> rest;
+    const size_t lim = m->waiting.front()->limit;
+    for (auto* p : m->waiting) (p->limit == lim ? batch : rest).push_back(p);
+    m->waiting.swap(rest);
+    q.unlock();
+    const int64_t nq = static_cast<int64_t>(batch.size());
+    std::vector<float> qbuf(static_cast<size_t>(nq) * m->dim);
+    for (int64_t i = 0; i < nq; ++i) std::memcpy(qbuf.data() + i * m->dim, batch[i]->query, sizeof(float) * m->dim);
+    std::vector<int64_t> oi(static_cast<size_t>(nq) * lim), oc(static_cast<size_t>(nq));
+    std::vector<double> od(static_cast<size_t>(nq) * lim);
+    int rc;
+    {
+      std::lock_guard<std::mutex> lk(m->mu);  // the index itself is single-threaded
+      rc = eps_search_batch(m->ix, qbuf.data(), nq, static_cast<int64_t>(lim), nullptr, 0, oi.data(), od.data(), oc.data(), nullptr);
+    }
+    q.lock();
+    for (int64_t i = 0; i < nq; ++i) {
+      auto* p = batch[i];
+      p->rc = rc;
+      if (rc == EPS_OK) {
+        p->count = oc[i];
+        std::memcpy(p->ids, oi.data() + i * lim, sizeof(int64_t) * lim);
+        std::memcpy(p->dists, od.data() + i * lim, sizeof(double) * lim);
+      }
+      p->done = true;
+    }
+    m->qcv.notify_all();
+  }
+  m->leader_active = false;
+  m->qcv.notify_all();  // a queued follower (if any) takes over as leader
+  *count = me.count;
+  return me.rc;
 }
 
 }  // namespace b200
@@ -147,7 +217,7 @@ Status VecSearchExecutor::Search(const VectorPtr query_data, vectordb::engine::T
   auto* m = reinterpret_cast<b200::Mirror*>(init_ids_[0]);
   if (m == nullptr || !std::holds_alternative<DenseVectorPtr>(query_data))
     return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: sparse-vector search is out of scope of the GPU path");
-  std::lock_guard<std::mutex> lk(m->mu);
+  std::unique_lock<std::mutex> lk(m->mu);
   const int64_t total = table_segment->record_number_;  // snapshot (:839)
   if (m->ix == nullptr) {
     m->capacity = static_cast<int64_t>(table_segment->size_limit_);
@@ -194,9 +264,17 @@ Status VecSearchExecutor::Search(const VectorPtr query_data, vectordb::engine::T
     distance_.resize(limit);
   }
   int64_t count = 0;
-  const int rc = eps_search_batch(m->ix, std::get<DenseVectorPtr>(query_data), 1, static_cast<int64_t>(limit),
-                                  nodes.empty() ? nullptr : nodes.data(), static_cast<int64_t>(nodes.size()),
-                                  search_result_.data(), distance_.data(), &count, nullptr);
+  int rc;
+  if (nodes.empty()) {
+    // hand the request to the mirror's batch former: release the mirror lock while queued so that the other
+    // executors of the pool (engine/db/execution/executor_pool.hpp) can join the same batch
+    lk.unlock();
+    rc = b200::SearchCoalesced(m, std::get<DenseVectorPtr>(query_data), limit, search_result_.data(), distance_.data(), &count);
+    lk.lock();
+  } else {
+    rc = eps_search_batch(m->ix, std::get<DenseVectorPtr>(query_data), 1, static_cast<int64_t>(limit), nodes.data(),
+                          static_cast<int64_t>(nodes.size()), search_result_.data(), distance_.data(), &count, nullptr);
+  }
   if (rc == EPS_ERR_UNSUPPORTED) return Status(NOT_IMPLEMENTED_ERROR, std::string("epsilla_b200: ") + eps_last_error());
   if (rc != EPS_OK) return b200::Fail("search");
   result_size = count;

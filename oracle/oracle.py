@@ -181,6 +181,8 @@ class Ref:
                                  C.c_void_p]
         L.ref_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_char_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
+        L.ref_save_graph.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64]
+        L.ref_load_graph.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64]
         L.ref_distance.restype = C.c_float
         L.ref_distance.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         L.ref_normalize.argtypes = [C.c_void_p, C.c_int64]
@@ -271,6 +273,14 @@ class Ref:
         off = np.ctypeslib.as_array(po, shape=(n + 1,)).copy()
         nb = np.ctypeslib.as_array(pn, shape=(int(off[n]),)).copy() if off[n] > 0 else np.zeros(0, np.int64)
         return n, off, nb, nav.value
+
+    def save_graph(self, directory, table_id=0, field_id=1):
+        if self.L.ref_save_graph(self.h, directory.encode(), table_id, field_id) != 0:
+            raise RuntimeError("SaveANNGraph failed")
+
+    def load_graph(self, directory, table_id=0, field_id=1):
+        if self.L.ref_load_graph(self.h, directory.encode(), table_id, field_id) != 0:
+            raise RuntimeError("ANNGraphSegment load failed")
 
     def make_executors(self, n_exec=1, T=1, L=500, iters=15, prefilter=False, counting=False):
         self.L_ = L

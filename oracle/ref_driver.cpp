@@ -25,6 +25,7 @@
 #include "db/table_segment_mvp.hpp"
 #include "db/vector.hpp"
 #include "query/expr/expr.hpp"
+#include "utils/common_util.hpp"
 
 using namespace vectordb;
 using namespace vectordb::engine;
@@ -210,6 +211,24 @@ int ref_search_batch(void* h, const float* queries, int64_t nq, int64_t limit, c
   for (int e = 1; e < ne; ++e) th.emplace_back(worker, e);
   worker(0);
   for (auto& t : th) t.join();
+  return 0;
+}
+
+// ann_graph_<field>.bin round trip through the reference's own writer / loader
+// (ANNGraphSegment::SaveANNGraph db/ann_graph_segment.cpp:156-199, loading ctor :39-98).
+int ref_save_graph(void* h, const char* dir, int64_t table_id, int64_t field_id) {
+  auto* c = static_cast<RefCtx*>(h);
+  server::CommonUtil::CreateDirectory(std::string(dir) + "/" + std::to_string(table_id));
+  auto st = c->ann->SaveANNGraph(dir, table_id, field_id, true);
+  return st.ok() ? 0 : -1;
+}
+int ref_load_graph(void* h, const char* dir, int64_t table_id, int64_t field_id) {
+  auto* c = static_cast<RefCtx*>(h);
+  try {
+    c->ann = std::make_shared<ANNGraphSegment>(std::string(dir), table_id, field_id);
+  } catch (...) {
+    return -1;
+  }
   return 0;
 }
 

@@ -73,3 +73,40 @@ def test_gpu_build_through_reference_surface(Drop):
     assert np.all(cnt == 10) and np.all(ids >= 100)
     truth = exact_topk(X[100:], Q, 10) + 100
     assert recall(ids, truth, 10) >= 0.97
+
+
+def test_concurrent_calls_are_coalesced_and_correct(Drop):
+    """16 executors hammered by 16 threads (ExecutorPool-style concurrency): single-query Search calls are
+    gathered into batched launches by the drop-in's batch former; every caller still gets its own answer."""
+    n, d, nq = 20000, 48, 512
+    X, Q = gen(n, d, 91), gen(nq, d, 92)
+    r = Drop("l2", d, n, [("ID", "int4")])
+    r.set_rows(X)
+    r.make_executors(16, 4, 500)      # n_indexed = 0 -> exact-scan branch
+    ids, ds, cnt = r.search_batch(Q, 10)
+    truth = exact_topk(X, Q, 10)
+    assert np.all(cnt == 10) and recall(ids, truth, 10) > 0.999
+    ids5, _, cnt5 = r.search_batch(Q[:64], 5)   # a different limit goes into its own batch
+    assert np.all(cnt5 == 5) and np.array_equal(ids5, ids[:64, :5])
+
+
+def test_graph_file_round_trip_through_reference_io(Drop, tmp_path):
+    """GPU-built graph -> reference SaveANNGraph (ann_graph_<field>.bin) -> reference loader -> GPU search."""
+    n, d, nq = 4000, 16, 16
+    X, Q = gen(n, d, 61), gen(nq, d, 62)
+    r = Drop("l2", d, n, [("ID", "int4")])
+    r.set_rows(X)
+    ni, off, nb, nav = r.build(threads=1)
+    r.make_executors(1, 1, 500)
+    before, bd, _ = r.search_batch(Q, 10)
+    r.save_graph(str(tmp_path))
+    path = tmp_path / "0" / "ann_graph_1.bin"
+    raw = np.fromfile(path, dtype=np.int64)       # layout: n, first_id, offsets[n+1], nbrs[E], nav (:171-184)
+    assert raw[0] == n and raw[1] == 0 and raw[-1] == nav and len(raw) == 2 + (n + 1) + off[-1] + 1
+    assert np.array_equal(raw[2:2 + n + 1], off) and np.array_equal(raw[2 + n + 1:-1], nb)
+    r2 = Drop("l2", d, n, [("ID", "int4")])
+    r2.set_rows(X)
+    r2.load_graph(str(tmp_path))
+    r2.make_executors(1, 1, 500)
+    after, ad, _ = r2.search_batch(Q, 10)
+    assert np.array_equal(before, after) and np.allclose(bd, ad)
