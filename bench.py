@@ -465,7 +465,11 @@ def main():
         flop = a.steps * rows * float(a.batch) * a.dim * 2.0
         ach = flop / (kernel_ms / 1000.0) / 1e12 if kernel_ms > 0 else 0.0
         peak = tf_peak / 2.0 if mode[2] == "tf32" else tf_peak
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        # DRAM bytes of ONE launch of the dominant kernel from the committed ncu capture of this workload
+        # (profiles/r01_ncu_tc_dist_fused_bf16_10Mx768.md: 4.04 GB read + 6.5 MB written for a 2.63 M-row launch,
+        # i.e. exactly the bf16 rows once); only quoted for the configuration it was captured on.
+        traffic = 4.039187e9 + 6.485504e6 if (mode[2] == "bf16" and rows == 10_000_000 and a.dim == 768 and a.batch == 1024) else None
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "kernel": "tc_dist_kernel (tcgen05 kind::%s, fused threshold select) + bf_select_kernel + rescore_kernel" % (
                     "tf32" if mode[2] == "tf32" else "f16/bf16"),
                 "peak_source": "%s bf16 sustained (%.0f TF/s)%s" % (peak_src, tf_peak, " / 2 for TF32" if mode[2] == "tf32" else ""),
