@@ -166,45 +166,49 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle/_ref = the reference's own sources compiled unmodified)
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_qps(X_host, Q_host, k, metric, graph=None, L=500, n_queries=32, repeats=1):
-    """Times VecSearchExecutor::Search on the host cores.  graph=None -> the brute-force branch (no graph, the
-    path the reference takes for an un-indexed table); else (n_indexed, offsets, nbrs, nav) -> graph search on
-    the SAME CSR the GPU used.  Returns (qps, cores, kind, sample, ids)."""
-    from oracle import oracle
-    cores = os.cpu_count() or 1
-    n, d = X_host.shape
-    kind = "reference" if oracle.have_ref() else "port"
-    Qs = np.ascontiguousarray(Q_host[:n_queries])
-    if kind == "reference":
-        r = oracle.Ref(metric, d, n, [("ID", "int4")])
-        r.vectors[:n] = X_host
-        r.set_row_count(n)
-        if graph is None:
-            n_exec = min(16, cores)
-            T = max(1, cores // n_exec)  # BruteForceSearch parallelises the distance loop with OpenMP
-            r.make_executors(n_exec, T, L)
+class CpuReference:
+    """VecSearchExecutor::Search of the reference on the host cores (oracle/_ref = the reference's own sources
+    compiled unmodified; the scalar C port only if that library did not travel).  graph=None -> the brute-force
+    branch (no graph: the path the reference takes for an un-indexed table); else (n_indexed, offsets, nbrs, nav)
+    -> graph search on the SAME CSR the GPU used.  The table is loaded once; search() is timed per call."""
+
+    def __init__(self, X_host, metric, graph=None, L=500, n_exec=None):
+        from oracle import oracle
+        self.cores = os.cpu_count() or 1
+        self.n, self.d = X_host.shape
+        self.kind = "reference" if oracle.have_ref() else "port"
+        self.metric, self.graph, self.L, self.X = metric, graph, L, X_host
+        if self.kind == "reference":
+            r = oracle.Ref(metric, self.d, self.n, [("ID", "int4")])
+            r.vectors[:self.n] = X_host
+            r.set_row_count(self.n)
+            if graph is None:
+                self.n_exec = min(n_exec or 16, self.cores)
+                self.T = max(1, self.cores // self.n_exec)  # BruteForceSearch parallelises its distance loop with OpenMP
+            else:
+                r.set_graph(*graph)
+                self.n_exec, self.T = self.cores, 1          # throughput-optimal: one executor per core (BASELINE.md 3.3b)
+            r.make_executors(self.n_exec, self.T, L)
+            self.r = r
         else:
-            r.set_graph(*graph)
-            n_exec, T = cores, 1        # throughput-optimal: one executor per core (BASELINE.md §3.3b)
-            r.make_executors(n_exec, T, L)
-        best = None
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            ids, ds, cnt = r.search_batch(Qs, k)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        used = n_exec * T
-        del r
-        return len(Qs) / best, used, kind, "%d queries of the step's batch over all %d rows, %d executors x %d threads" % (
-            len(Qs), n, n_exec, T), ids
-    port = oracle.Port()
-    t0 = time.perf_counter()
-    kw = dict(metric=metric, vectors=X_host, queries=Qs, limit=k, L=L)
-    if graph is not None:
-        kw.update(n_indexed=graph[0], offsets=graph[1], nbrs=graph[2], nav=graph[3])
-    ids, ds, cnt, _ = port.search_batch(**kw)
-    dt = time.perf_counter() - t0
-    return len(Qs) / dt, 1, kind, "%d queries over all %d rows, scalar C port, 1 thread" % (len(Qs), n), ids
+            self.port = oracle.Port()
+            self.n_exec, self.T = 1, 1
+
+    def search(self, Q_host, k):
+        Qs = np.ascontiguousarray(Q_host)
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            ids, ds, cnt = self.r.search_batch(Qs, k)
+        else:
+            kw = dict(metric=self.metric, vectors=self.X, queries=Qs, limit=k, L=self.L)
+            if self.graph is not None:
+                kw.update(n_indexed=self.graph[0], offsets=self.graph[1], nbrs=self.graph[2], nav=self.graph[3])
+            ids, ds, cnt, _ = self.port.search_batch(**kw)
+        dt = time.perf_counter() - t0
+        return len(Qs) / dt, ids
+
+    def describe(self, nq):
+        return "%d queries of the step's batch over all %d rows, %d executors x %d threads" % (nq, self.n, self.n_exec, self.T)
 
 
 def run_reference_arm(a):
@@ -218,17 +222,15 @@ def run_reference_arm(a):
     X = gen_table(a.rows, a.dim, a.dist, 42, dev)
     Xh = X.cpu().numpy()
     del X
-    cores = os.cpu_count() or 1
+    nq = max(1, min(a.cpu_queries // 4, a.batch))  # bounded sample per step: the whole run ends within minutes
+    ref = CpuReference(Xh, a.metric, None, 500, n_exec=nq)  # one executor per sampled query, all host threads busy
     vals = []
-    sample = ""
-    kind = "reference"
-    used = cores
     for s in range(a.warmup + a.steps):
-        Q = gen_queries(a.batch, a.dim, a.dist, 43 + s, dev).cpu().numpy()
-        nq = min(a.cpu_queries, a.batch)
-        qps, used, kind, sample, _ = cpu_reference_qps(Xh, Q, a.k, a.metric, None, 500, nq)
+        Q = gen_queries(a.batch, a.dim, a.dist, 43 + s * 64, dev).cpu().numpy()
+        qps, _ = ref.search(Q[:nq], a.k)
         if s >= a.warmup:
             vals.append(qps)
+    kind, used, sample = ref.kind, ref.n_exec * ref.T, ref.describe(nq)
     v = float(np.mean(vals))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps,
@@ -512,7 +514,10 @@ def main():
             if mode[0] == "graph":
                 graph = ix.get_graph()
                 L = mode[1]
-            qps, cores, kind, sample, cids = cpu_reference_qps(Xh, Qh, a.k, a.metric, graph, L, min(a.cpu_queries, a.batch))
+            nqc = min(a.cpu_queries, a.batch)
+            ref = CpuReference(Xh, a.metric, graph, L)
+            qps, cids = ref.search(Qh[:nqc], a.k)
+            cores, kind, sample = ref.n_exec * ref.T, ref.kind, ref.describe(nqc)
             agree = float(np.mean([len(set(cids[i].tolist()) & set(truth[i].tolist())) / a.k for i in range(len(cids))]))
             out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample,
                                    "ids_agree_with_gpu": agree}
