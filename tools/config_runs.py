@@ -24,7 +24,37 @@ def timed(fn, reps=3):
     return (time.perf_counter() - t0) / reps, st
 
 
-if which == "c3":
+if which == "c1":
+    # C1: brute-force L2 top-10, 10k x 128 f32, batch = 1, through the host-buffer API, next to the reference CPU path
+    from oracle.oracle import Ref
+    rows, dim, k = 10_000, 128, 10
+    rng = np.random.default_rng(42)
+    X = rng.random((rows, dim), dtype=np.float32)
+    Q = rng.random((512, dim), dtype=np.float32)
+    ix = vectordb_b200.Index("l2", dim, host_vectors=X)
+    ix.sync_rows(rows)
+    for q in Q[:32]:
+        ix.search(q, k, want_stats=False)
+    t0 = time.perf_counter()
+    got = [ix.search(q, k, want_stats=False)[0][0] for q in Q]
+    gpu_qps = len(Q) / (time.perf_counter() - t0)
+    out = {"config": "C1 10000x128 L2 brute force, batch=1, top-10 (one eps_search_batch call per query, host buffers)",
+           "gpu_qps_sequential_calls": gpu_qps, "gpu_latency_us": 1e6 / gpu_qps}
+    try:
+        r = Ref("l2", dim, rows, [("ID", "int4")])
+        r.set_rows(X)
+        for T in (1, 8):
+            r.make_executors(1, T, 500)
+            for q in Q[:8]:
+                r.search(q, k)
+            t0 = time.perf_counter()
+            ref = [r.search(q, k)[0] for q in Q]
+            out["reference_cpu_qps_T%d" % T] = len(Q) / (time.perf_counter() - t0)
+        out["ids_identical"] = float(np.mean([np.array_equal(a, b) for a, b in zip(got, ref)]))
+    except Exception as e:
+        out["reference"] = "unavailable: %r" % (e,)
+    print(json.dumps(out))
+elif which == "c3":
     dim, nq, k = 768, 4096, 100
     X = gen_table(rows, dim, "uniform", 42, dev)
     Q = gen_queries(nq, dim, "uniform", 43, dev)

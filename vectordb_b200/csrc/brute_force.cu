@@ -493,11 +493,11 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
   if (chunk > n) chunk = ((n + 3) / 4) * 4;
   EPS_TRY(ix->s_dist.reserve(static_cast<size_t>(nq) * chunk * 4));
   float* D = ix->s_dist.as<float>();
-  // splits: enough CTAs to fill the machine, each >= 4096 elements
+  // splits: enough CTAs to fill the machine, each >= 16384 elements
   int nsplit = 1;
   {
     int64_t want = (2ll * ix->num_sms + nq - 1) / nq;
-    int64_t maxs = std::max<int64_t>(1, chunk / 4096);
+    int64_t maxs = std::max<int64_t>(1, chunk / 16384);  // a split must be worth its extra merge launch
     nsplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, maxs), 64)));
     if (use_tc) nsplit = 1;  // the running threshold is read from the single per-query state
   }

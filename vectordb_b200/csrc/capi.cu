@@ -159,14 +159,14 @@ static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t 
   const bool brute = ix->prefilter || ix->force_brute || n_indexed < 512;  // BruteforceThreshold (hpp:28)
   eps_stats local;
   std::memset(&local, 0, sizeof(local));
-  EPS_CUDA(cudaEventRecord(ix->ev[1], ix->stream));
+  if (stats) EPS_CUDA(cudaEventRecord(ix->ev[1], ix->stream));
   if (brute) {
     if (limit > 8192) return fail(EPS_ERR_UNSUPPORTED, "limit above 8192 is not supported");
     const int64_t k = limit;
     EPS_TRY(ix->s_topk.reserve(static_cast<size_t>(nq) * k * 8));
     EPS_TRY(brute_force_topk(ix, d_queries, nq, 0, total, k, d_prog, &h_prog, ix->prefilter,
                              ix->s_topk.as<unsigned long long>(), &local));
-    EPS_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
+    if (stats) EPS_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
     // :857 prefilter: min(size, limit); :864 brute: min(size, limit, L_local)
     const int64_t cap = (ix->prefilter || ix->force_brute) ? limit : std::min<int64_t>(limit, ix->L_local);
     EPS_TRY(finalize_keys(ix, ix->s_topk.as<unsigned long long>(), nq, k, limit, cap, d_ids, d_dists, d_counts));
@@ -177,7 +177,7 @@ static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t 
     EPS_TRY(ix->s_queue.reserve(static_cast<size_t>(nq) * L * 8));
     EPS_TRY(graph_search(ix, d_queries, nq, L, ix->s_queue.as<unsigned long long>(), &local));
     ix->graph_counters_pending = true;
-    EPS_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
+    if (stats) EPS_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
     const unsigned long long* d_tail = nullptr;
     int64_t tail_k = 0;
     if (total > n_indexed) {  // :885-900
@@ -262,6 +262,7 @@ void eps_index_destroy(eps_index* h) {
                          &ix->s_visited, &ix->s_queue, &ix->s_tail, &ix->s_out_ids, &ix->s_out_dists,
                          &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist, &ix->s_xnorm, &ix->s_qnorm, &ix->s_coarse, &ix->s_thr, &ix->s_cand, &ix->s_cand_cnt, &ix->s_bf16, &ix->s_qbf16};
   for (auto* b : bufs) b->release();
+  if (ix->h_out) cudaFreeHost(ix->h_out);
   for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ix->stream);
   delete ix;
@@ -400,9 +401,10 @@ int eps_search_batch_device(eps_index* h, const float* d_queries, int64_t nq, in
   if (!ix || !d_queries || !d_out_ids || !d_out_dists || !d_out_counts)
     return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument");
   EPS_TRY(eps::check_device(ix->device));
-  EPS_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
+  if (stats) EPS_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
   EPS_TRY(eps::search_device(ix, d_queries, nq, limit, filter, n_filter, d_out_ids, d_out_dists, d_out_counts, stats));
-  EPS_CUDA(cudaEventRecord(ix->ev[3], ix->stream));
+  if (stats) EPS_CUDA(cudaEventRecord(ix->ev[3], ix->stream));
+  if (!stats) ix->graph_counters_pending = false;
   if (sync || stats) {
     EPS_CUDA(cudaStreamSynchronize(ix->stream));
     if (stats) {
@@ -422,22 +424,33 @@ int eps_search_batch(eps_index* h, const float* queries, int64_t nq, int64_t lim
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix || !queries || !out_ids || !out_dists || !out_counts) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument");
   if (nq <= 0) return EPS_OK;
+  if (limit < 1) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "limit must be >= 1");
   EPS_TRY(eps::check_device(ix->device));
-  EPS_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
+  if (stats) EPS_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
+  // one device block [ids | counts | dists] and one pinned host mirror of it: a single D2H copy per call
+  const size_t n_ids = static_cast<size_t>(nq) * limit;
+  const size_t off_cnt = n_ids * 8, off_dist = off_cnt + static_cast<size_t>(nq) * 8, total = off_dist + n_ids * 4;
   EPS_TRY(ix->s_queries.reserve(static_cast<size_t>(nq) * ix->dim * 4));
-  EPS_TRY(ix->s_out_ids.reserve(static_cast<size_t>(nq) * limit * 8));
-  EPS_TRY(ix->s_out_dists.reserve(static_cast<size_t>(nq) * limit * 4));
-  EPS_TRY(ix->s_out_counts.reserve(static_cast<size_t>(nq) * 8));
+  EPS_TRY(ix->s_out_ids.reserve(total));
+  if (ix->h_out_cap < total) {
+    if (ix->h_out) cudaFreeHost(ix->h_out);
+    ix->h_out = nullptr;
+    ix->h_out_cap = 0;
+    EPS_CUDA(cudaHostAlloc(&ix->h_out, total, cudaHostAllocDefault));
+    ix->h_out_cap = total;
+  }
+  unsigned char* d_blk = ix->s_out_ids.as<unsigned char>();
   EPS_CUDA(cudaMemcpyAsync(ix->s_queries.p, queries, static_cast<size_t>(nq) * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
-  EPS_TRY(eps::search_device(ix, ix->s_queries.as<float>(), nq, limit, filter, n_filter, ix->s_out_ids.as<int64_t>(),
-                             ix->s_out_dists.as<float>(), ix->s_out_counts.as<int64_t>(), stats));
-  std::vector<float> hd(static_cast<size_t>(nq) * limit);
-  EPS_CUDA(cudaMemcpyAsync(out_ids, ix->s_out_ids.p, static_cast<size_t>(nq) * limit * 8, cudaMemcpyDeviceToHost, ix->stream));
-  EPS_CUDA(cudaMemcpyAsync(hd.data(), ix->s_out_dists.p, hd.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
-  EPS_CUDA(cudaMemcpyAsync(out_counts, ix->s_out_counts.p, static_cast<size_t>(nq) * 8, cudaMemcpyDeviceToHost, ix->stream));
-  EPS_CUDA(cudaEventRecord(ix->ev[3], ix->stream));
+  EPS_TRY(eps::search_device(ix, ix->s_queries.as<float>(), nq, limit, filter, n_filter, reinterpret_cast<int64_t*>(d_blk),
+                             reinterpret_cast<float*>(d_blk + off_dist), reinterpret_cast<int64_t*>(d_blk + off_cnt), stats));
+  EPS_CUDA(cudaMemcpyAsync(ix->h_out, d_blk, total, cudaMemcpyDeviceToHost, ix->stream));
+  if (stats) EPS_CUDA(cudaEventRecord(ix->ev[3], ix->stream));
   EPS_CUDA(cudaStreamSynchronize(ix->stream));
-  for (size_t i = 0; i < hd.size(); ++i) out_dists[i] = static_cast<double>(hd[i]);  // distance_ is vector<double> (hpp:52)
+  const unsigned char* hb = static_cast<const unsigned char*>(ix->h_out);
+  std::memcpy(out_ids, hb, n_ids * 8);
+  std::memcpy(out_counts, hb + off_cnt, static_cast<size_t>(nq) * 8);
+  const float* hd = reinterpret_cast<const float*>(hb + off_dist);
+  for (size_t i = 0; i < n_ids; ++i) out_dists[i] = static_cast<double>(hd[i]);  // distance_ is vector<double> (hpp:52)
   if (stats) {
     if (ix->graph_counters_pending) { EPS_TRY(eps::read_graph_counters(ix, stats)); ix->graph_counters_pending = false; }
     float ms = 0.f;
@@ -446,6 +459,7 @@ int eps_search_batch(eps_index* h, const float* queries, int64_t nq, int64_t lim
     cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]);
     stats->total_ms += ms;
   }
+  ix->graph_counters_pending = false;
   return EPS_OK;
 }
 

@@ -480,6 +480,8 @@ __global__ void __launch_bounds__(128, 7) graph_search_kernel_wide(GS2Args a, in
           if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = nb;
           if (e == kEll - 1) atomicOr(&s_more, 1 << ci);
         }
+        const unsigned vb = __ballot_sync(kFull, nb >= 0);  // ncur * kEll is a multiple of 32: warp-uniform trip count
+        if (lane == 0 && vb) atomicAdd(&s_nedge, static_cast<unsigned long long>(__popc(vb)));
       }
       __syncthreads();  // (2)
       if (tid == 0) s_nexp += static_cast<unsigned long long>(ncur);
@@ -575,6 +577,7 @@ __global__ void __launch_bounds__(128, 7) graph_search_kernel_wide(GS2Args a, in
   if (tid == 0) {
     atomicAdd(&a.stats[0], s_ndist);
     atomicAdd(&a.stats[1], s_nexp);
+    atomicAdd(&a.stats[2], s_nedge);
   }
 }
 
