@@ -295,6 +295,8 @@ int eps_index_adopt_device_rows(eps_index* h, const float* d_vectors, int64_t n_
   ix->n_rows = n_rows;
   if (n_rows > ix->capacity) ix->capacity = n_rows;
   ix->vec4 = (ix->dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_vectors) & 15) == 0);
+  ix->xnorm_rows = 0;  // derived mirrors (row norms, bf16 copy) belong to the previous table
+  ix->bf16_rows = 0;
   return EPS_OK;
 }
 
