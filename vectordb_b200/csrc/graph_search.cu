@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(128, 7) graph_search_kernel_v2(GS2Args a) {
 // merged back) — like that mode it is NOT bit-identical to the sequential order (W = 1, kernels above, is);
 // it trades that for W-fold fewer dependent round trips per query.  Same queue / visited / bound rules.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kWideMax = 4;
+constexpr int kWideMax = 8;
 constexpr int kWCap = kWideMax * kEll;  // fresh / candidate slots per iteration
 
 __global__ void __launch_bounds__(128, 7) graph_search_kernel_wide(GS2Args a, int W) {
