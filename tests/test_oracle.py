@@ -148,3 +148,43 @@ def test_filter_eval_vs_reference(port, have_ref):
         for row in range(n):
             for dist in (0.25, 0.75):
                 assert port.filter_eval(nodes, r.attrs, r.stride, row, dist) == r.filter_eval(e, row, dist), (e, row)
+
+
+def test_add_into_queue_properties(port):
+    """AddIntoQueue (vec_search_executor.cpp:75-117): the bounded queue stays sorted by (distance,id), holds the
+    best `cap` entries ever offered, never holds an id twice when the duplicate lands on its twin, and the
+    returned position is where the entry went (cap = rejected / duplicate)."""
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    for cap in (1, 4, 16):
+        ids = np.zeros(cap + 1, np.int64); ds = np.zeros(cap + 1, np.float32); ck = np.zeros(cap + 1, np.uint8)
+        size = C.c_int64(0)
+        offered = {}
+        for step in range(200):
+            i = int(rng.integers(0, 40)); d = float(np.float32(rng.integers(0, 12)) / 4)
+            dup_of_existing = i in offered and offered[i] == d
+            r = port.L.port_add_into_queue(ids.ctypes.data, ds.ctypes.data, ck.ctypes.data, C.byref(size), cap, i, C.c_float(d))
+            n = size.value
+            assert 0 <= n <= cap
+            keys = list(zip(ds[:n].tolist(), ids[:n].tolist()))
+            assert keys == sorted(keys), "queue must stay sorted by (distance, id)"
+            if r < cap:
+                assert ids[r] == i and ds[r] == np.float32(d)
+                offered[i] = d
+            elif dup_of_existing and (d, i) in keys:
+                pass  # duplicate rejected (:91-95)
+        best = sorted(keys)
+        assert keys == best[:n]
+
+
+def test_search_is_deterministic_and_L_monotone(port, golden):
+    """The T=1 search is a pure function of its inputs, and a longer queue never evaluates fewer rows."""
+    g = golden["rand2k"]
+    kw = dict(metric="l2", vectors=g["stored_l2"][:2000], queries=g["queries_l2"][:4], limit=10, n_indexed=2000,
+              offsets=g["offsets_l2"], nbrs=g["nbrs_l2"].astype(np.int64), nav=int(g["nav_l2"]), total_rows=2000)
+    a = port.search_batch(L=128, **kw)
+    b = port.search_batch(L=128, **kw)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[3] == b[3]
+    c = port.search_batch(L=512, **kw)
+    assert c[3][0] >= a[3][0]
+    assert np.all(c[1][:, 0] <= a[1][:, 0] + 1e-12)  # the best distance can only improve with a longer queue
