@@ -366,3 +366,22 @@ def test_large_batch_top100_with_filter(vdb, port):
     gids, gds, gcnt, _ = ix.search(Q[:64], k, filter_nodes=nodes)  # post-filter: only the best L are considered
     assert np.all(gcnt <= k) and np.all(attr[gids[gids >= 0]] < 10)
     ix.close()
+
+
+def test_cta_pair_tensor_core_variant_matches(vdb):
+    """EPS_TC_2CTA=1 selects the tcgen05 cta_group::2 kernel (two CTAs per 256x256 tile): same answers."""
+    import os
+    n, d, nq, k = 400000, 64, 256, 10
+    X, Q = gen(n, d, 601), gen(nq, d, 602)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.config(500, 500, force_brute=True)
+    ix.set_coarse("bf16")
+    want, wd, _, _ = ix.search(Q, k)
+    os.environ["EPS_TC_2CTA"] = "1"
+    try:
+        got, gd, _, _ = ix.search(Q, k)
+    finally:
+        del os.environ["EPS_TC_2CTA"]
+    assert np.array_equal(got, want) and np.allclose(gd, wd)
+    ix.close()

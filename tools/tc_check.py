@@ -27,22 +27,27 @@ if __name__ == "__main__":
         ids, ds, ms = run(rows, dim, nq, k, metric)
         np.savez(sys.argv[7], ids=ids, ds=ds, ms=ms)
         sys.exit(0)
-    cases = [(20000, 64, 256, 10, "l2"), (50000, 768, 1024, 10, "l2"), (33333, 100, 300, 100, "ip"), (40000, 128, 512, 10, "cosine"),
-             (1000000, 768, 1024, 10, "l2"), (4000000, 768, 1024, 10, "l2")]
+    cases = [(300000, 96, 300, 100, "ip"), (1000000, 768, 1024, 10, "l2"), (4000000, 768, 1024, 10, "l2")]
+    if len(sys.argv) > 1 and sys.argv[1] == "all":
+        cases = [(20000, 64, 256, 10, "l2"), (50000, 768, 1024, 10, "l2"), (33333, 100, 300, 100, "ip"),
+                 (40000, 128, 512, 10, "cosine")] + cases
     for c in cases:
         out = {}
-        for tag, env in (("tc", {"EPS_COARSE": "tf32"}), ("bf16", {"EPS_COARSE": "bf16"}), ("simt", {"EPS_COARSE": "fp32"})):
+        for tag, env in (("tc", {"EPS_COARSE": "tf32"}), ("bf16", {"EPS_COARSE": "bf16"}), ("bf16_2cta", {"EPS_COARSE": "bf16", "EPS_TC_2CTA": "1"}),
+                         ("tf32_2cta", {"EPS_COARSE": "tf32", "EPS_TC_2CTA": "1"}), ("simt", {"EPS_COARSE": "fp32"})):
             f = "/tmp/tc_%s.npz" % tag
             e = dict(os.environ); e.update(env)
-            r = subprocess.run(["timeout", "120", sys.executable, __file__, "child"] + [str(x) for x in c] + [f], env=e,
+            r = subprocess.run(["timeout", "90", sys.executable, __file__, "child"] + [str(x) for x in c] + [f], env=e,
                                capture_output=True, text=True)
             if r.returncode != 0:
-                print("case", c, tag, "FAILED rc", r.returncode, r.stderr[-400:]); out = None; break
+                print("case", c, tag, "FAILED rc", r.returncode, r.stderr[-300:]); continue
             out[tag] = np.load(f)
-        if out is None:
+        if "simt" not in out:
             continue
         res = {"case": c, "simt_ms": round(float(out["simt"]["ms"]), 3)}
-        for t in ("tc", "bf16"):
+        for t in ("tc", "bf16", "bf16_2cta", "tf32_2cta"):
+            if t not in out:
+                continue
             res[t + "_ids_equal"] = float((out[t]["ids"] == out["simt"]["ids"]).mean())
             res[t + "_set_recall"] = float(np.mean([len(set(a) & set(b)) / len(b) for a, b in zip(out[t]["ids"], out["simt"]["ids"])]))
             res[t + "_ms"] = round(float(out[t]["ms"]), 3)
