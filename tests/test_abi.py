@@ -59,3 +59,26 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dp, f), errors="replace").read()
                 m = bad.search(src)
                 assert m is None, "%s references the oracle: %r" % (f, m.group(0))
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as strict C99 (no C++ / torch types) and link against the
+    library by symbol name."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "epsilla_b200.h"\n'
+        "#include <stddef.h>\n"
+        "int main(void) {\n"
+        "  eps_filter_node n; eps_stats s; eps_build_params b; eps_index* ix = NULL;\n"
+        "  (void)n; (void)s; (void)b;\n"
+        "  if (sizeof(eps_filter_node) != 64 || sizeof(eps_stats) != 64) return 2;\n"
+        "  /* no device in this container: creation must fail loudly, never fall back */\n"
+        "  return eps_index_create(&ix, EPS_METRIC_L2, 8, NULL, 0, 0) == EPS_OK && eps_device_count() == 0 ? 3 : 0;\n"
+        "}\n")
+    exe = tmp_path / "abi"
+    lib_dir = os.path.join(ROOT, "vectordb_b200")
+    _lib()
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", lib_dir, "-lepsilla_b200", "-Wl,-rpath," + lib_dir])
+    assert subprocess.call([str(exe)]) == 0
