@@ -56,6 +56,11 @@ struct TcArgs {
   const uint32_t* pass;         // deleted / static-filter bitmap relative to pass_base (may be null)
   int64_t pass_base;
   int cand_cap;
+  // EPS_TC_DEBUG (developer timing aid, results are garbage when set): bit 0 = stop issuing TMA loads after the
+  // first ring fill, bit 1 = skip the MMAs, bit 2 = skip the epilogue's TMEM reads.  Brackets which of the three
+  // engines bounds the kernel (tools/tc_limiter.py).
+  int debug;
+  int epi_pipelined;  // EPS_TC_EPI: 1 = overlap the TMEM read of the next chunk with the compare of this one
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -132,6 +137,66 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// one warp reads its 32 TMEM lanes x 32 fp32 columns (asynchronous until tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue work on one 32-column chunk of the accumulator (v[j] = dot(row, query q0+j) for this thread's row).
+__device__ __forceinline__ void epi_chunk(const TcArgs& a, const uint32_t (&v)[32], int q0, bool row_ok, float xn, int64_t i,
+                                          int64_t row_abs, const float* thr_s, const float* qn_s) {
+  if (a.D == nullptr) {
+    // ---- fused selection: 2 instructions per element (FFMA + compare), survivors are rare ----
+    if (row_ok) {
+      const float m = a.metric == EPS_METRIC_L2 ? -2.0f : -1.0f;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 ct = *reinterpret_cast<const float4*>(thr_s + q0 + 4 * j4);
+        const float t0 = fmaf(m, __uint_as_float(v[4 * j4 + 0]), xn), t1 = fmaf(m, __uint_as_float(v[4 * j4 + 1]), xn);
+        const float t2 = fmaf(m, __uint_as_float(v[4 * j4 + 2]), xn), t3 = fmaf(m, __uint_as_float(v[4 * j4 + 3]), xn);
+        if ((t0 < ct.x) | (t1 < ct.y) | (t2 < ct.z) | (t3 < ct.w)) {
+          const float tt[4] = {t0, t1, t2, t3};
+          const float cc[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (tt[u] < cc[u]) {
+              const int q = q0 + 4 * j4 + u;
+              float d = tt[u];
+              if (a.metric == EPS_METRIC_L2) d = fmaxf(d + qn_s[q], 0.f);
+              else if (a.metric == EPS_METRIC_COSINE) d = 1.0f + d;
+              const int slot = atomicAdd(&a.cand_cnt[q], 1);
+              if (slot < a.cand_cap) a.cand[static_cast<int64_t>(q) * a.cand_cap + slot] = make_key(d, static_cast<uint32_t>(row_abs));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ---- distance tile to global memory (first chunk: seeds the running thresholds) ----
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int q = q0 + j;
+      if (row_ok && q < a.nq) {
+        const float dot = __uint_as_float(v[j]);
+        float d;
+        if (a.metric == EPS_METRIC_L2) d = fmaxf(xn + qn_s[q] - 2.0f * dot, 0.f);
+        else if (a.metric == EPS_METRIC_COSINE) d = 1.0f - dot;
+        else d = -dot;
+        a.D[static_cast<int64_t>(q) * a.ldd + i] = d;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, TcArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -168,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
       const float th = a.thr[i];
       c = a.metric == EPS_METRIC_L2 ? th - qn : (a.metric == EPS_METRIC_COSINE ? th - 1.0f : th);
     }
-    thr_s[i] = c;
+    thr_s[i] = a.debug ? -INFINITY : c;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -188,6 +253,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
+            if ((a.debug & 1) && it >= kTcStages) { mbar_arrive(full0 + 8 * s); continue; }
             mbar_expect_tx(full0 + 8 * s, kTcStageBytes);
             const uint32_t sa = stage0 + s * kTcStageBytes;
             tma_load_2d(sa, &tmA, kb * a.kb_elems, row0, full0 + 8 * s);
@@ -216,6 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
             const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + kTcABytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // 4 MMAs per 128-byte block: K = 8 tf32 / 16 bf16 = 32 bytes = +2 (16-B units)
+              if (a.debug & 2) break;
               if (bf16) umma_issue<true>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
               else umma_issue<false>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
             }
@@ -243,61 +310,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
         const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
         mbar_wait(tfull0 + 8 * acc, aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lq) << 16) + acc * kTcBN;
+        const int qbase = qt * kTcBN;
+        if (a.debug & 4) {
+          // timing aid: leave the accumulator unread
+        } else if (a.epi_pipelined) {
+          // software-pipelined: the TMEM read of chunk c+1 is in flight while chunk c is compared (two register
+          // sets; TMEM reads are 64 B/clk per SM, so an un-overlapped load + compare per chunk is epilogue-bound)
+          uint32_t va[32], vb[32];
+          tmem_ld32(va, taddr0);
 #pragma unroll 1
-        for (int c = 0; c < kTcBN / 32; ++c) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lq) << 16) + acc * kTcBN + c * 32;
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int q0 = qt * kTcBN + c * 32;
-          if (a.D == nullptr) {
-            // ---- fused selection: 2 instructions per element (FFMA + compare), survivors are rare ----
-            if (row_ok) {
-              const float m = a.metric == EPS_METRIC_L2 ? -2.0f : -1.0f;
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 ct = *reinterpret_cast<const float4*>(thr_s + q0 + 4 * j4);
-                const float t0 = fmaf(m, __uint_as_float(v[4 * j4 + 0]), xn), t1 = fmaf(m, __uint_as_float(v[4 * j4 + 1]), xn);
-                const float t2 = fmaf(m, __uint_as_float(v[4 * j4 + 2]), xn), t3 = fmaf(m, __uint_as_float(v[4 * j4 + 3]), xn);
-                if ((t0 < ct.x) | (t1 < ct.y) | (t2 < ct.z) | (t3 < ct.w)) {
-                  const float tt[4] = {t0, t1, t2, t3};
-                  const float cc[4] = {ct.x, ct.y, ct.z, ct.w};
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    if (tt[u] < cc[u]) {
-                      const int q = q0 + 4 * j4 + u;
-                      float d = tt[u];
-                      if (a.metric == EPS_METRIC_L2) d = fmaxf(d + qn_s[q], 0.f);
-                      else if (a.metric == EPS_METRIC_COSINE) d = 1.0f + d;
-                      const int slot = atomicAdd(&a.cand_cnt[q], 1);
-                      if (slot < a.cand_cap) a.cand[static_cast<int64_t>(q) * a.cand_cap + slot] = make_key(d, static_cast<uint32_t>(row_abs));
-                    }
-                  }
-                }
-              }
-            }
-          } else {
-            // ---- distance tile to global memory (first chunk: seeds the running thresholds) ----
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int q = q0 + j;
-              if (row_ok && q < a.nq) {
-                const float dot = __uint_as_float(v[j]);
-                float d;
-                if (a.metric == EPS_METRIC_L2) d = fmaxf(xn + qn_s[q] - 2.0f * dot, 0.f);
-                else if (a.metric == EPS_METRIC_COSINE) d = 1.0f - dot;
-                else d = -dot;
-                a.D[static_cast<int64_t>(q) * a.ldd + i] = d;
-              }
-            }
+          for (int c = 0; c < kTcBN / 32; c += 2) {
+            tmem_ld_wait();
+            tmem_ld32(vb, taddr0 + (c + 1) * 32);
+            epi_chunk(a, va, qbase + c * 32, row_ok, xn, i, row_abs, thr_s, qn_s);
+            tmem_ld_wait();
+            if (c + 2 < kTcBN / 32) tmem_ld32(va, taddr0 + (c + 2) * 32);
+            epi_chunk(a, vb, qbase + (c + 1) * 32, row_ok, xn, i, row_abs, thr_s, qn_s);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < kTcBN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(v, taddr0 + c * 32);
+            tmem_ld_wait();
+            epi_chunk(a, v, qbase + c * 32, row_ok, xn, i, row_abs, thr_s, qn_s);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -662,6 +699,10 @@ int tc_launch_distances(Index* ix, int64_t row_start, int64_t n, const float* d_
   }
   a.n_row_tiles = static_cast<int>((n + kTcBM - 1) / kTcBM);
   a.n_q_tiles = static_cast<int>((nq + kTcBN - 1) / kTcBN);
+  const char* dbg = getenv("EPS_TC_DEBUG");
+  a.debug = dbg ? atoi(dbg) : 0;
+  const char* epi = getenv("EPS_TC_EPI");
+  a.epi_pipelined = epi ? atoi(epi) : 0;
   const bool two_cta = getenv("EPS_TC_2CTA") != nullptr && a.n_row_tiles >= 2 * ix->num_sms;
   if (two_cta) {
     // CTA pairs: B tensor map box = 128 queries (each CTA stages half of the 256-query block)
