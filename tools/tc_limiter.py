@@ -22,7 +22,7 @@ def main():
     ref = None
     plan = [(0, 0), (1, 0), (2, 0), (4, 0), (5, 0), (6, 0), (0, 0)]
     if os.environ.get("TC_LIMITER_PLAN") == "epi":
-        plan = [(0, 0), (0, 1), (1, 1), (2, 1), (0, 0), (0, 1)]
+        plan = [(0, 0), (0, 1), (0, 2), (1, 2), (2, 2), (0, 0), (0, 2)]
     for mode, epi in plan:
         os.environ["EPS_TC_DEBUG"] = str(mode)
         os.environ["EPS_TC_EPI"] = str(epi)
@@ -35,7 +35,7 @@ def main():
             ids = oi.cpu()
             if ref is None: ref = ids
             else: out["mode0_ids_equal_first"] = bool((ids == ref).all()) and out.get("mode0_ids_equal_first", True)
-        key = {0: "all", 1: "no_tma", 2: "no_mma", 4: "no_epilogue", 5: "mma_only", 6: "tma_only"}[mode] + ("_epi1" if epi else "")
+        key = {0: "all", 1: "no_tma", 2: "no_mma", 4: "no_epilogue", 5: "mma_only", 6: "tma_only"}[mode] + ("_epi%d" % epi if epi else "")
         while key + "_ms" in out: key += "_again"
         out[key + "_ms"] = round(min(ms[1:]), 3)
         out[key + "_TFs"] = round(out["flops"] / min(ms[1:]) / 1e9, 1)

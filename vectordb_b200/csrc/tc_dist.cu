@@ -60,7 +60,8 @@ struct TcArgs {
   // first ring fill, bit 1 = skip the MMAs, bit 2 = skip the epilogue's TMEM reads.  Brackets which of the three
   // engines bounds the kernel (tools/tc_limiter.py).
   int debug;
-  int epi_pipelined;  // EPS_TC_EPI: 1 = overlap the TMEM read of the next chunk with the compare of this one
+  int epi_pipelined;  // EPS_TC_EPI: 1 = overlap the TMEM read of the next chunk with the compare of this one (measured: no
+                      // gain), 2 = experimental branch-light compare (epi_chunk_fast); 0 / unset = the validated default
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -197,6 +198,46 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const uint32_t (&v)[3
   }
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 r;
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
+}
+// EXPERIMENTAL (EPS_TC_EPI=2, fused mode only; not yet measured on the GPU): branch-light form of the fused
+// selection.  The thresholds of the chunk come from true LDS loads issued before the TMEM wait, all 32 compares
+// fold into four predicate chains and ONE rarely-taken branch per chunk guards the candidate push (epi_chunk
+// branches once per 4 elements behind a dependent generic load: 64 serialised round trips per 128x256 tile).
+__device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const uint32_t (&v)[32], const float4 (&ct)[8], int q0, bool row_ok,
+                                               float xn, int64_t row_abs, const float* qn_s) {
+  const float m = a.metric == EPS_METRIC_L2 ? -2.0f : -1.0f;
+  bool h0 = false, h1 = false, h2 = false, h3 = false;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    h0 |= fmaf(m, __uint_as_float(v[4 * j4 + 0]), xn) < ct[j4].x;
+    h1 |= fmaf(m, __uint_as_float(v[4 * j4 + 1]), xn) < ct[j4].y;
+    h2 |= fmaf(m, __uint_as_float(v[4 * j4 + 2]), xn) < ct[j4].z;
+    h3 |= fmaf(m, __uint_as_float(v[4 * j4 + 3]), xn) < ct[j4].w;
+  }
+  if ((h0 | h1 | h2 | h3) && row_ok) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float cc[4] = {ct[j4].x, ct[j4].y, ct[j4].z, ct[j4].w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float t = fmaf(m, __uint_as_float(v[4 * j4 + u]), xn);
+        if (t < cc[u]) {
+          const int q = q0 + 4 * j4 + u;
+          float d = t;
+          if (a.metric == EPS_METRIC_L2) d = fmaxf(d + qn_s[q], 0.f);
+          else if (a.metric == EPS_METRIC_COSINE) d = 1.0f + d;
+          const int slot = atomicAdd(&a.cand_cnt[q], 1);
+          if (slot < a.cand_cap) a.cand[static_cast<int64_t>(q) * a.cand_cap + slot] = make_key(d, static_cast<uint32_t>(row_abs));
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, TcArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -314,6 +355,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
         const int qbase = qt * kTcBN;
         if (a.debug & 4) {
           // timing aid: leave the accumulator unread
+        } else if (a.epi_pipelined == 2 && a.D == nullptr) {
+          const uint32_t thr_addr = smem_u32(thr_s);
+#pragma unroll 1
+          for (int c = 0; c < kTcBN / 32; ++c) {
+            uint32_t v[32];
+            float4 ct[8];
+            tmem_ld32(v, taddr0 + c * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) ct[j4] = lds128(thr_addr + static_cast<uint32_t>(qbase + c * 32 + 4 * j4) * 4u);
+            tmem_ld_wait();
+            epi_chunk_fast(a, v, ct, qbase + c * 32, row_ok, xn, row_abs, qn_s);
+          }
         } else if (a.epi_pipelined) {
           // software-pipelined: the TMEM read of chunk c+1 is in flight while chunk c is compared (two register
           // sets; TMEM reads are 64 B/clk per SM, so an un-overlapped load + compare per chunk is epilogue-bound)
