@@ -143,10 +143,23 @@ static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t 
   EPS_TRY(lower_filter(filter, n_filter, &h_prog));
   const FilterProg* d_prog = nullptr;
   if (h_prog.n > 0) {
-    if (!ix->d_attrs) {
-      bool needs_attrs = false;
-      for (int i = 0; i < h_prog.n; ++i) needs_attrs |= h_prog.nodes[i].field_offset >= 0;
-      if (needs_attrs) return fail(EPS_ERR_INVALID_ARGUMENT, "filter reads attributes but eps_index_set_attrs was not called");
+    // every attribute read must stay inside the mirrored row-major attribute table
+    for (int i = 0; i < h_prog.n; ++i) {
+      const FNode& nd = h_prog.nodes[i];
+      int width = 0;
+      switch (nd.type) {
+        case NT_Int1Attr: case NT_BoolAttr: width = 1; break;
+        case NT_Int2Attr: width = 2; break;
+        case NT_Int4Attr: case NT_FloatAttr: width = 4; break;
+        case NT_Int8Attr: case NT_DoubleAttr: width = 8; break;
+        default: break;
+      }
+      if (width == 0 || nd.field_offset < 0) continue;  // constants, operators, the @distance pseudo-field
+      if (!ix->d_attrs) return fail(EPS_ERR_INVALID_ARGUMENT, "filter reads attributes but eps_index_set_attrs was not called");
+      if (static_cast<int64_t>(nd.field_offset) + width > ix->attr_stride)
+        return fail(EPS_ERR_INVALID_ARGUMENT, "filter field offset lies outside the attribute row");
+      if (ix->attr_rows < ix->n_rows)
+        return fail(EPS_ERR_INVALID_ARGUMENT, "attribute mirror has fewer rows than the vector mirror (call eps_index_set_attrs)");
     }
     EPS_TRY(ix->s_filter.reserve(sizeof(FilterProg)));
     EPS_CUDA(cudaMemcpyAsync(ix->s_filter.p, &h_prog, sizeof(FilterProg), cudaMemcpyHostToDevice, ix->stream));
@@ -311,6 +324,10 @@ int eps_index_set_graph(eps_index* h, int64_t n_indexed, const int64_t* offsets,
   if (n_indexed >= (1ll << 31)) return eps::fail(EPS_ERR_UNSUPPORTED, "more than 2^31 indexed rows");
   if (nav < 0 || nav >= n_indexed) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "navigation point out of range");
   const int64_t e = offsets[n_indexed];
+  if (offsets[0] != 0 || e < 0) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "offset table must start at 0 and end at the edge count");
+  for (int64_t i = 0; i < n_indexed; ++i)
+    if (offsets[i + 1] < offsets[i]) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "offset table is not monotonic");
+  if (e > 0 && !nbrs) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null neighbor list");
   std::vector<int32_t> nb32(static_cast<size_t>(e > 0 ? e : 1));
   for (int64_t i = 0; i < e; ++i) {
     if (nbrs[i] < 0 || nbrs[i] >= n_indexed) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "neighbor id out of range");
@@ -476,29 +493,36 @@ int eps_merge_shards_device(int device, const int64_t* d_ids, const float* d_dis
 int eps_normalize(int device, float* host_vectors, int64_t nq, int64_t dim) {
   EPS_TRY(eps::check_device(device));
   if (nq <= 0) return EPS_OK;
+  if (!host_vectors || dim < 1) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null vectors / bad dim");
+  const size_t bytes = static_cast<size_t>(nq) * dim * 4;
   float* d = nullptr;
-  EPS_CUDA(cudaMalloc(&d, static_cast<size_t>(nq) * dim * 4));
-  cudaMemcpy(d, host_vectors, static_cast<size_t>(nq) * dim * 4, cudaMemcpyHostToDevice);
-  int rc = eps::normalize_rows_device(nullptr, d, nq, dim);
-  cudaMemcpy(host_vectors, d, static_cast<size_t>(nq) * dim * 4, cudaMemcpyDeviceToHost);
+  EPS_CUDA(cudaMalloc(&d, bytes));
+  cudaError_t e = cudaMemcpy(d, host_vectors, bytes, cudaMemcpyHostToDevice);
+  int rc = EPS_OK;
+  if (e == cudaSuccess) rc = eps::normalize_rows_device(nullptr, d, nq, dim);
+  if (e == cudaSuccess && rc == EPS_OK) e = cudaMemcpy(host_vectors, d, bytes, cudaMemcpyDeviceToHost);
   cudaFree(d);
+  if (e != cudaSuccess) return eps::fail(EPS_ERR_CUDA, cudaGetErrorString(e));
   return rc;
 }
 
 int eps_pair_distances(int device, int metric, const float* a, const float* b, int64_t n, int64_t dim, float* out) {
   EPS_TRY(eps::check_device(device));
   if (n <= 0) return EPS_OK;
+  if (!a || !b || !out || dim < 1) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument / bad dim");
   float *da = nullptr, *db = nullptr, *dout = nullptr;
   const size_t bytes = static_cast<size_t>(n) * dim * 4;
-  EPS_CUDA(cudaMalloc(&da, bytes));
-  EPS_CUDA(cudaMalloc(&db, bytes));
-  EPS_CUDA(cudaMalloc(&dout, static_cast<size_t>(n) * 4));
-  cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
-  cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
-  eps::pair_distance_kernel<<<static_cast<unsigned>((n * 32 + 127) / 128), 128>>>(metric, dim % 4 == 0 ? 1 : 0, da, db, n,
-                                                                                 static_cast<int>(dim), dout);
-  cudaError_t e = cudaDeviceSynchronize();
-  cudaMemcpy(out, dout, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMalloc(&da, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&db, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, static_cast<size_t>(n) * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    eps::pair_distance_kernel<<<static_cast<unsigned>((n * 32 + 127) / 128), 128>>>(metric, dim % 4 == 0 ? 1 : 0, da, db, n,
+                                                                                   static_cast<int>(dim), dout);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost);
   cudaFree(da); cudaFree(db); cudaFree(dout);
   if (e != cudaSuccess) return eps::fail(EPS_ERR_CUDA, cudaGetErrorString(e));
   return EPS_OK;
