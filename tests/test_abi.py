@@ -82,3 +82,22 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                            str(src), "-o", str(exe), "-L", lib_dir, "-lepsilla_b200", "-Wl,-rpath," + lib_dir])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_dropin_library_binds_reference_symbols_to_the_gpu_path():
+    """integration/_build/libepsilla_ref_b200.so = the reference's own objects with three symbols replaced: each must be
+    defined exactly once (strong), and the library must import the C ABI from libepsilla_b200.so (no CPU body left)."""
+    import subprocess
+    so = os.path.join(ROOT, "integration", "_build", "libepsilla_ref_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("drop-in not built (needs /root/reference at build time)")
+    dyn = subprocess.check_output(["nm", "-D", "-C", so], text=True)
+    for sym in ("VecSearchExecutor::Search(", "VecSearchExecutor::VecSearchExecutor(long, long,",
+                "ANNGraphSegment::BuildFromVectorTable("):
+        strong = {l.split()[0] for l in dyn.splitlines() if sym in l and " T " in l}
+        weak = [l for l in dyn.splitlines() if sym in l and " W " in l]
+        assert len(strong) == 1 and not weak, (sym, strong, weak)
+    for imp in ("eps_search_batch", "eps_index_build", "eps_index_get_graph", "eps_index_set_graph", "eps_index_sync_rows"):
+        assert any(l.strip().startswith("U " + imp) for l in dyn.splitlines()), imp
+    needed = subprocess.check_output(["readelf", "-d", so], text=True)
+    assert "libepsilla_b200.so" in needed
