@@ -68,7 +68,7 @@ def parse():
 # synthetic data (identical bits on every rank / in the reference arm: torch CPU generator is not used for
 # the 30 GB table — it is generated on device in 1M-row chunks from a seeded Philox stream)
 # ------------------------------------------------------------------------------------------------------
-def gen_table(rows, dim, dist, seed, device):
+def gen_table(rows, dim, dist, seed, device, centers_n=1024):
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -77,20 +77,20 @@ def gen_table(rows, dim, dist, seed, device):
     if dist == "cluster":
         gc = torch.Generator(device=device)
         gc.manual_seed(44)
-        centers = torch.rand((1024, dim), generator=gc, device=device)
+        centers = torch.rand((centers_n, dim), generator=gc, device=device)
     step = 1_000_000
     for r0 in range(0, rows, step):
         r1 = min(rows, r0 + step)
         if dist == "uniform":
             X[r0:r1].uniform_(0.0, 1.0, generator=g)
         else:
-            lab = torch.randint(0, 1024, (r1 - r0,), generator=g, device=device)
+            lab = torch.randint(0, centers_n, (r1 - r0,), generator=g, device=device)
             X[r0:r1].normal_(0.0, 0.1, generator=g)
             X[r0:r1] += centers[lab]
     return X
 
 
-def gen_queries(n, dim, dist, seed, device):
+def gen_queries(n, dim, dist, seed, device, centers_n=1024):
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -98,8 +98,8 @@ def gen_queries(n, dim, dist, seed, device):
         return torch.rand((n, dim), generator=g, device=device)
     gc = torch.Generator(device=device)
     gc.manual_seed(44)
-    centers = torch.rand((1024, dim), generator=gc, device=device)
-    lab = torch.randint(0, 1024, (n,), generator=g, device=device)
+    centers = torch.rand((centers_n, dim), generator=gc, device=device)
+    lab = torch.randint(0, centers_n, (n,), generator=g, device=device)
     return centers[lab] + 0.1 * torch.randn((n, dim), generator=g, device=device)
 
 

@@ -13,8 +13,9 @@ Ls = [int(x) for x in (sys.argv[5] if len(sys.argv) > 5 else "128,512,2048").spl
 exact_below = int(os.environ.get("EXACT_BELOW", "60000"))
 nq, k = 1024, 10
 dev = torch.device("cuda", 0)
-X = gen_table(rows, dim, dist, 42, dev)
-Q = gen_queries(nq, dim, dist, 43, dev)
+centers = int(os.environ.get("CENTERS", "1024"))
+X = gen_table(rows, dim, dist, 42, dev, centers)
+Q = gen_queries(nq, dim, dist, 43, dev, centers)
 ix = vectordb_b200.Index("l2", dim, capacity=rows)
 ix.adopt_device_rows(X.data_ptr(), rows)
 oi = torch.empty((nq, k), dtype=torch.int64, device=dev); od = torch.empty((nq, k), dtype=torch.float32, device=dev)

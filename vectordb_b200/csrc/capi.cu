@@ -174,19 +174,22 @@ static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t 
   std::memset(&local, 0, sizeof(local));
   if (stats) EPS_CUDA(cudaEventRecord(ix->ev[1], ix->stream));
   if (brute) {
-    if (limit > 8192) return fail(EPS_ERR_UNSUPPORTED, "limit above 8192 is not supported");
-    const int64_t k = limit;
+    // :857 prefilter: min(size, limit); :864 brute: min(size, limit, L_local).  Only that many entries are ever
+    // emitted, so the exact top-k is taken for the EFFECTIVE k (a large `limit` on a small table is legal).
+    const int64_t cap = (ix->prefilter || ix->force_brute) ? limit : std::min<int64_t>(limit, ix->L_local);
+    const int64_t k = std::max<int64_t>(1, std::min<int64_t>(cap, total));
+    if (k > 8192) return fail(EPS_ERR_UNSUPPORTED, "more than 8192 results per query from the exact scan are not supported");
     EPS_TRY(ix->s_topk.reserve(static_cast<size_t>(nq) * k * 8));
     EPS_TRY(brute_force_topk(ix, d_queries, nq, 0, total, k, d_prog, &h_prog, ix->prefilter,
                              ix->s_topk.as<unsigned long long>(), &local));
     if (stats) EPS_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
-    // :857 prefilter: min(size, limit); :864 brute: min(size, limit, L_local)
-    const int64_t cap = (ix->prefilter || ix->force_brute) ? limit : std::min<int64_t>(limit, ix->L_local);
     EPS_TRY(finalize_keys(ix, ix->s_topk.as<unsigned long long>(), nq, k, limit, cap, d_ids, d_dists, d_counts));
     local.kernel_launches += 1;
   } else {
     const int64_t L = std::min<int64_t>(ix->L_master, n_indexed);  // Q1 clamp
-    const int64_t search_limit = std::min<int64_t>(std::min<int64_t>(n_indexed, limit), ix->L_local);  // :872
+    // :872 min(n_indexed, limit, L_local); the queue row holds L entries, so the merge window is clamped to it
+    // (the reference ties L_local to L_master through setSearchQueueSize; the C ABI accepts them separately)
+    const int64_t search_limit = std::min<int64_t>(std::min<int64_t>(std::min<int64_t>(n_indexed, limit), ix->L_local), L);
     EPS_TRY(ix->s_queue.reserve(static_cast<size_t>(nq) * L * 8));
     EPS_TRY(graph_search(ix, d_queries, nq, L, ix->s_queue.as<unsigned long long>(), &local));
     ix->graph_counters_pending = true;
@@ -194,7 +197,9 @@ static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t 
     const unsigned long long* d_tail = nullptr;
     int64_t tail_k = 0;
     if (total > n_indexed) {  // :885-900
-      tail_k = std::min<int64_t>(std::min<int64_t>(limit, total - n_indexed), 8192);
+      // only the first search_limit slots can receive tail entries (:894-900)
+      tail_k = std::min<int64_t>(std::min<int64_t>(limit, total - n_indexed), search_limit);
+      if (tail_k > 8192) return fail(EPS_ERR_UNSUPPORTED, "more than 8192 tail results per query are not supported");
       EPS_TRY(ix->s_tail.reserve(static_cast<size_t>(nq) * tail_k * 8));
       EPS_TRY(brute_force_topk(ix, d_queries, nq, n_indexed, total, tail_k, d_prog, &h_prog, false,
                                ix->s_tail.as<unsigned long long>(), &local));
@@ -302,9 +307,13 @@ int eps_index_adopt_device_rows(eps_index* h, const float* d_vectors, int64_t n_
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix || !d_vectors) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument");
   EPS_TRY(eps::check_device(ix->device));
+  if (n_rows < 0 || n_rows >= (1ll << 31)) return eps::fail(EPS_ERR_UNSUPPORTED, "row count must be in [0, 2^31): keys carry 31-bit ids");
   if (ix->owns_vectors && ix->d_vectors) cudaFree(ix->d_vectors);
   ix->owns_vectors = false;
   ix->d_vectors = const_cast<float*>(d_vectors);
+  // state derived from the previous table: gathered seed rows always, the graph itself if it no longer fits
+  ix->seed_rows_L = 0;
+  if (ix->n_indexed > n_rows) eps::free_graph(ix);
   ix->n_rows = n_rows;
   if (n_rows > ix->capacity) ix->capacity = n_rows;
   ix->vec4 = (ix->dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_vectors) & 15) == 0);
@@ -419,6 +428,7 @@ int eps_search_batch_device(eps_index* h, const float* d_queries, int64_t nq, in
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix || !d_queries || !d_out_ids || !d_out_dists || !d_out_counts)
     return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument");
+  if (nq <= 0) return EPS_OK;  // nothing launched: no events to read back
   EPS_TRY(eps::check_device(ix->device));
   if (stats) EPS_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
   EPS_TRY(eps::search_device(ix, d_queries, nq, limit, filter, n_filter, d_out_ids, d_out_dists, d_out_counts, stats));

@@ -1,7 +1,6 @@
 // K2 — batched best-first graph search.  SURVEY.md §8a rows A4-A8.
 //
-// What the reference computes (engine/db/execution/vec_search_executor.cpp, IntraQueryThreads = 1, the
-// only configuration in which it is a pure function of its inputs — SURVEY.md §5/§8c):
+// What the reference computes (engine/db/execution/vec_search_executor.cpp):
 //   InitializeSetLPara (:446-485)  seed the queue with the L query-independent init ids, mark them
 //                                  visited, sort by (distance,id);
 //   SearchImpl (:518-715)          repeatedly expand the first unchecked queue entry;
@@ -9,36 +8,67 @@
 //                                  dist > worst-in-queue, else AddIntoQueue (:75-117, sorted insert with
 //                                  eviction); return the lowest insert position r;
 //   k = (r <= k) ? r : k+1 (:648-652); stop when no unchecked entry is left.
+//   IntraQueryThreads > 1 (:601-698): the master deals unchecked candidates to workers, which expand them
+//   concurrently against a slightly stale bound and merge back — not a pure function of the inputs.
 // The queue after one expansion is the top-L by (distance,id) of {queue ∪ unvisited neighbours}, whatever
 // the insertion order, and r is the final position of the smallest inserted entry; so evaluating all
 // neighbour distances of a vertex in parallel and merging them at once is equivalent.
 //
-// Mapping: a persistent grid, one CTA per in-flight query (queries are claimed from an atomic counter),
-// the sorted queue and the query vector in shared memory, one warp per neighbour row (coalesced 128-bit
-// streaming loads, warp-shuffle reduction), a per-CTA visited bitmap in global memory (L2-resident),
-// block-parallel rank-and-shift merge instead of the reference's memmove insert.
+// Mapping (ONE kernel, two modes):
+//   * persistent grid, one CTA (128 threads) per in-flight query, queries claimed from an atomic counter;
+//   * the sorted queue (L 64-bit keys), the query vector, a FIFO of fresh neighbour ids and a RING of row
+//     slots live in shared memory;
+//   * a neighbour row is brought HBM -> shared memory by ONE 1-D bulk async copy (TMA engine,
+//     cp.async.bulk + mbarrier complete_tx) issued by a single lane: no registers are held across the wait,
+//     every free ring slot is in flight at once, and the adjacency reads + visited-bitmap atomics of the NEXT
+//     candidates run while the rows of the previous ones land;
+//   * distances: 8-lane teams read the landed row and the query as float4 from shared memory, FMA, 3 shuffle
+//     steps; accepted keys (key < worst-in-queue) go to a small pending buffer that is merged into the sorted
+//     queue by a block-parallel rank-and-shift when it fills (or after every expansion in exact mode);
+//   * adjacency: fixed-stride rows of 64 int32 ids (one 256-byte read from the vertex id; longer rows
+//     continue in the CSR); visited: one bitmap per in-flight query in global memory, atomicOr test-and-set,
+//     cleared by the CTA after the query like the reference clears its vector<bool> (:711-714).
+// exact mode (search width 1): one candidate per iteration, rows consumed and merged before the next pick —
+//   the visit order, results and distance-evaluation counts of the reference at IntraQueryThreads = 1.
+// wide mode (width W = 2/4/8): up to W candidates are picked per iteration from queue ∪ pending while the rows
+//   of the previous iteration are still in flight — the device analogue of IntraQueryThreads > 1; like that
+//   mode it is not bit-identical to the sequential order.
 #include <cstdlib>
 
+#include "async.cuh"
 #include "internal.h"
 
 namespace eps {
 
-constexpr int kCH = 64;  // neighbours handled per merge round
+constexpr int kEll = 64;        // adjacency ids per fixed-stride row
+constexpr int kGsThreads = 128;
+constexpr int kMaxW = 8;        // candidates picked per iteration (upper bound)
+constexpr int kPC = 128;        // accepted keys pending their merge (= one key per thread in the merge)
+constexpr int kFC = 1024;       // fresh-id FIFO capacity (power of two >= kMaxW * kEll + kMaxR + kGsThreads)
+constexpr int kMaxR = 32;       // ring slots (upper bound; one issuing lane per slot)
+constexpr int kRounds = kMaxW * kEll / kGsThreads;  // adjacency slots per thread
 
 struct GSArgs {
   const float* vectors;
   const int64_t* offsets;
   const int32_t* nbrs;
+  const int32_t* ell;             // [n x kEll], -1 padded
   const int32_t* init_ids;
+  const float* seed_dist;         // [nq x seed_ld] distances of the seed set (dense tile product)
   const float* queries;
-  uint32_t* visited;            // [slots x visited_words]
+  uint32_t* visited;              // [slots x visited_words]
   unsigned long long* out_queue;  // [nq x L]
   int* work_counter;
-  unsigned long long* stats;    // n_dist, n_expand, n_edges, n_seed
+  unsigned long long* stats;      // n_dist, n_expand, n_edges
   int64_t visited_words;
+  int64_t seed_ld;
   int dim, metric, vec4;
   int L, Lp;
   int nq;
+  int W;                          // candidates per iteration (1 in exact mode)
+  int exact;
+  int R;                          // ring slots
+  int slot_bytes;                 // ring slot pitch (row bytes, multiple of 16); 0 when rows are not staged
 };
 
 __device__ __forceinline__ int lb_masked(const unsigned long long* a, int n, unsigned long long key) {
@@ -50,21 +80,129 @@ __device__ __forceinline__ int lb_masked(const unsigned long long* a, int n, uns
   return lo;
 }
 
-__global__ void __launch_bounds__(128, 6) graph_search_kernel(GSArgs a) {
-  extern __shared__ __align__(16) unsigned char gs_smem[];
-  unsigned long long* queue = reinterpret_cast<unsigned long long*>(gs_smem);          // [Lp]
-  unsigned long long* cand = queue + a.Lp;                                             // [kCH] accepted, unsorted
-  unsigned long long* cs = cand + kCH;                                                 // [kCH] accepted, sorted
-  float* qv = reinterpret_cast<float*>(cs + kCH);                                      // [dim padded to 4]
-  int* pos = reinterpret_cast<int*>(qv + ((a.dim + 3) & ~3));                          // [kCH]
-  int* fresh = pos + kCH;                                                              // [kCH]
-  __shared__ int s_q, s_cur, s_nfresh, s_nacc, s_pmin;
-  __shared__ unsigned long long s_ndist, s_nexp, s_nedge;
+// 8-lane team partial of one row against the query (both in shared memory when VEC4; the row in global
+// memory otherwise).  Lane tl covers float4 chunks tl, tl+8, ...
+template <bool L2>
+__device__ __forceinline__ float team_partial_vec4(const float4* __restrict__ row, const float4* __restrict__ q, int dim4, int tl) {
+  float a0 = 0.f, a1 = 0.f;
+  int c = tl;
+  for (; c + 8 < dim4; c += 16) {
+    const float4 x0 = row[c], y0 = q[c], x1 = row[c + 8], y1 = q[c + 8];
+    if (L2) {
+      float d;
+      d = x0.x - y0.x; a0 = fmaf(d, d, a0); d = x0.y - y0.y; a0 = fmaf(d, d, a0);
+      d = x0.z - y0.z; a0 = fmaf(d, d, a0); d = x0.w - y0.w; a0 = fmaf(d, d, a0);
+      d = x1.x - y1.x; a1 = fmaf(d, d, a1); d = x1.y - y1.y; a1 = fmaf(d, d, a1);
+      d = x1.z - y1.z; a1 = fmaf(d, d, a1); d = x1.w - y1.w; a1 = fmaf(d, d, a1);
+    } else {
+      a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+      a1 = fmaf(x1.x, y1.x, a1); a1 = fmaf(x1.y, y1.y, a1); a1 = fmaf(x1.z, y1.z, a1); a1 = fmaf(x1.w, y1.w, a1);
+    }
+  }
+  if (c < dim4) {
+    const float4 x0 = row[c], y0 = q[c];
+    if (L2) {
+      float d;
+      d = x0.x - y0.x; a0 = fmaf(d, d, a0); d = x0.y - y0.y; a0 = fmaf(d, d, a0);
+      d = x0.z - y0.z; a0 = fmaf(d, d, a0); d = x0.w - y0.w; a0 = fmaf(d, d, a0);
+    } else {
+      a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+    }
+  }
+  return a0 + a1;
+}
+template <bool L2>
+__device__ __forceinline__ float team_partial_scalar(const float* __restrict__ row, const float* __restrict__ q, int dim, int tl) {
+  float a = 0.f;
+  for (int i = tl; i < dim; i += 8) {
+    const float x = __ldg(row + i), y = q[i];
+    if (L2) { const float d = x - y; a = fmaf(d, d, a); } else { a = fmaf(x, y, a); }
+  }
+  return a;
+}
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+// Block-wide merge of the m (<= kPC) pending keys into the sorted queue qa[0..L): sort by counting, binary-search
+// the insertion points, shift the tail in place in super-tiles of 8 keys per thread (each key moves right by the
+// number of pending keys that precede it), drop the keys into the holes.  Entries pushed past L are evicted
+// (AddIntoQueue's drop-worst, :104-108).  Returns the lowest insert position through *s_cursor (min).
+__device__ __forceinline__ void merge_pending(unsigned long long* qa, unsigned long long* pend, unsigned long long* cs, int* pos,
+                                              int m, int L, int* s_npend, int* s_cursor) {
+  const int tid = threadIdx.x;
+  if (tid < m) {
+    const unsigned long long key = pend[tid];
+    int r = 0;
+    for (int j = 0; j < m; ++j) r += ((pend[j] & kKeyMask) < (key & kKeyMask));
+    cs[r] = key;
+  }
+  __syncthreads();
+  if (tid < m) pos[tid] = lb_masked(qa, L, cs[tid] & kKeyMask);
+  __syncthreads();
+  const int p0 = pos[0];
+  for (int hi = L; hi > p0; hi -= 8 * kGsThreads) {
+    unsigned long long kreg[8];
+    int dreg[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = hi - 1 - (u * kGsThreads + tid);
+      dreg[u] = L;
+      if (j >= p0) {
+        kreg[u] = qa[j];
+        int sft = 0;
+        if (m <= 8) { for (int i = 0; i < m; ++i) sft += (pos[i] <= j); }
+        else { int lo = 0, up = m; while (lo < up) { const int mid = (lo + up) >> 1; if (pos[mid] <= j) lo = mid + 1; else up = mid; } sft = lo; }
+        dreg[u] = j + sft;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (dreg[u] < L) qa[dreg[u]] = kreg[u];
+    __syncthreads();
+  }
+  if (tid < m) {
+    const int f = pos[tid] + tid;
+    if (f < L) qa[f] = cs[tid];
+  }
+  if (tid == 0) {
+    *s_npend = 0;
+    if (p0 < *s_cursor) *s_cursor = p0;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kGsThreads, 4) graph_search_kernel(GSArgs a) {
+  extern __shared__ __align__(128) unsigned char gs_smem[];
+  const int dim4p = (a.dim + 3) & ~3;
+  unsigned char* ring = gs_smem;                                                                   // [R][slot_bytes]
+  unsigned long long* qa = reinterpret_cast<unsigned long long*>(ring + static_cast<size_t>(a.R) * a.slot_bytes);  // [Lp]
+  unsigned long long* pend = qa + a.Lp;                                                            // [kPC]
+  unsigned long long* cs = pend + kPC;                                                             // [kPC]
+  unsigned long long* bars = cs + kPC;                                                             // [kMaxR]
+  float* qv = reinterpret_cast<float*>(bars + kMaxR);                                              // [dim4p]
+  int* pos = reinterpret_cast<int*>(qv + dim4p);                                                   // [kPC]
+  int* fifo = pos + kPC;                                                                           // [kFC]
+  int* slot_id = fifo + kFC;                                                                       // [kMaxR]
+  __shared__ int s_q, s_ncur, s_cursor, s_npend, s_ncont;
+  __shared__ int s_cid[kMaxW];
+  __shared__ int s_wcnt[kRounds][kGsThreads / 32];
+  __shared__ long long s_cont_e[kMaxW], s_cont_end[kMaxW];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int team = lane >> 3, tl = lane & 7;
+  const unsigned team_mask = 0xFFu << (team * 8);
+  const unsigned lane_lt = (1u << lane) - 1u;
+  const int L = a.L, R = a.R, W = a.W;
+  const bool staged = a.slot_bytes > 0;
+  const uint32_t ring0 = smem_u32(ring), bar0 = smem_u32(bars);
+  const uint32_t row_bytes = static_cast<uint32_t>(a.dim) * 4u;
   uint32_t* visited = a.visited + static_cast<int64_t>(blockIdx.x) * a.visited_words;
-  const int L = a.L;
-  if (tid == 0) { s_ndist = 0; s_nexp = 0; s_nedge = 0; }
+
+  if (tid == 0) {
+    for (int s = 0; s < R; ++s) mbar_init(bar0 + 8 * s, 1);
+    mbar_fence_init();
+  }
+  // rows that went through the ring since the kernel started: slot = g % R, mbarrier phase parity = (g / R) & 1
+  uint32_t n_issued = 0, n_consumed = 0;
+  unsigned long long st_ndist = 0, st_nexp = 0, st_nedge = 0;
 
   for (;;) {
     __syncthreads();
@@ -72,513 +210,230 @@ __global__ void __launch_bounds__(128, 6) graph_search_kernel(GSArgs a) {
     __syncthreads();
     const int q = s_q;
     if (q >= a.nq) break;
-    for (int i = tid; i < a.dim; i += blockDim.x) qv[i] = a.queries[static_cast<int64_t>(q) * a.dim + i];
-    for (int i = L + tid; i < a.Lp; i += blockDim.x) queue[i] = kKeyInf;
-    if (tid == 0) { s_nfresh = 0; s_nacc = 0; }
-    __syncthreads();
 
-    // ---- seed (InitializeSetLPara) ----
-    for (int i = tid; i < L; i += blockDim.x) {
-      uint32_t id = static_cast<uint32_t>(a.init_ids[i]);
-      atomicOr(&visited[id >> 5], 1u << (id & 31));
+    // ---- seed (InitializeSetLPara): precomputed distances of the query-independent seed set ----
+    for (int i = tid; i < a.dim; i += kGsThreads) qv[i] = a.queries[static_cast<int64_t>(q) * a.dim + i];
+    for (int i = a.dim + tid; i < dim4p; i += kGsThreads) qv[i] = 0.f;
+    for (int i = tid; i < a.Lp; i += kGsThreads) {
+      unsigned long long key = kKeyInf;
+      if (i < L) {
+        const uint32_t id = static_cast<uint32_t>(a.init_ids[i]);
+        atomicOr(&visited[id >> 5], 1u << (id & 31));
+        key = make_key(a.seed_dist[static_cast<int64_t>(q) * a.seed_ld + i], id);
+      }
+      qa[i] = key;
     }
-    for (int i = warp; i < L; i += nwarps) {
-      const int id = a.init_ids[i];
-      float d = warp_distance(a.metric, a.vec4 != 0, a.vectors + static_cast<int64_t>(id) * a.dim, qv, a.dim, lane);
-      if (lane == 0) queue[i] = make_key(d, static_cast<uint32_t>(id));
-    }
+    if (tid == 0) { s_npend = 0; s_ncont = 0; s_cursor = 0; s_ncur = 0; }
     __syncthreads();
-    block_bitonic_sort(queue, a.Lp);
+    block_bitonic_sort(qa, a.Lp);
+    if (tid == 0) st_ndist += static_cast<unsigned long long>(L);
+    uint32_t fifo_head = 0, fifo_tail = 0;  // fresh ids: [head, tail) not yet issued to the ring
 
     // ---- best-first loop (SearchImpl) ----
-    int k = 0;
     for (;;) {
-      if (warp == 0) {
-        int found = -1;
-        for (int p = k; p < L; p += 32) {
-          int idx = p + lane;
-          bool un = idx < L && !(queue[idx] & kCheckedBit);
-          unsigned b = __ballot_sync(kFull, un);
-          if (b) { found = p + __ffs(b) - 1; break; }
-        }
-        if (lane == 0) {
-          s_cur = found;
-          s_pmin = L;
-          if (found >= 0) queue[found] |= kCheckedBit;
-        }
-      }
-      __syncthreads();
-      const int cur = s_cur;
-      if (cur < 0) break;
-      const int c = static_cast<int>(key_id(queue[cur]));
-      const int64_t e0 = a.offsets[c], e1 = a.offsets[c + 1];
-      __syncthreads();  // everyone holds cur before warp 0 may publish the next one
-      if (tid == 0) { ++s_nexp; s_nedge += static_cast<unsigned long long>(e1 - e0); }
-
-      for (int64_t eb = e0; eb < e1; eb += kCH) {
-        const int cnt = static_cast<int>(min(static_cast<int64_t>(kCH), e1 - eb));
-        // visited test-and-set (ExpandOneCandidate :403-406)
-        if (tid < cnt) {
-          const uint32_t nb = static_cast<uint32_t>(a.nbrs[eb + tid]);
-          const uint32_t bit = 1u << (nb & 31);
-          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
-          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = static_cast<int>(nb);
-        }
-        __syncthreads();
-        const int nfresh = s_nfresh;
-        const unsigned long long bound = queue[L - 1] & kKeyMask;  // live worst entry (:546)
-        for (int i = warp; i < nfresh; i += nwarps) {
-          const int nb = fresh[i];
-          float d = warp_distance(a.metric, a.vec4 != 0, a.vectors + static_cast<int64_t>(nb) * a.dim, qv, a.dim, lane);
-          if (lane == 0) {
-            unsigned long long key = make_key(d, static_cast<uint32_t>(nb));
-            if (key < bound) cand[atomicAdd(&s_nacc, 1)] = key;  // dist > bound rejected (:424); ties by id
-          }
-        }
-        __syncthreads();
-        const int m = s_nacc;
-        if (m > 0) {
-          // 1. sort the accepted candidates (rank by counting; keys are distinct)
-          for (int i = tid; i < m; i += blockDim.x) {
-            const unsigned long long key = cand[i];
-            int r = 0;
-            for (int j = 0; j < m; ++j) r += (cand[j] < key);
-            cs[r] = key;
-          }
-          __syncthreads();
-          // 2. insertion points in the current queue
-          for (int i = tid; i < m; i += blockDim.x) pos[i] = lb_masked(queue, L, cs[i]);
-          __syncthreads();
-          const int p0 = pos[0];
-          // 3. shift old entries right by the number of candidates that precede them, top tile first
-          for (int hi = L; hi > p0; hi -= blockDim.x) {
-            const int j = hi - 1 - tid;
-            unsigned long long key = 0;
-            int dest = L;
-            if (j >= p0) {
-              key = queue[j];
-              int lo = 0, up = m;  // s = #{i : pos[i] <= j}
-              while (lo < up) { int mid = (lo + up) >> 1; if (pos[mid] <= j) lo = mid + 1; else up = mid; }
-              dest = j + lo;
+      // A runs when the ring cannot be kept full from the backlog alone (wide) / when the previous expansion
+      // has been fully consumed and merged (exact)
+      const bool want = a.exact ? (fifo_tail == fifo_head && n_issued == n_consumed)
+                                : (fifo_tail - fifo_head) < static_cast<uint32_t>(R);
+      int ncur = 0, ncont = 0;
+      if (want) {
+        // -- A0: pick up to W unchecked candidates, smallest first, from queue ∪ pending (warp 0) --
+        if (warp == 0) {
+          int cnt = 0;
+          if (s_ncont == 0) {
+            const int np = s_npend;
+            int sp = s_cursor;
+            unsigned long long pk = ~0ull;  // smallest unchecked pending key (recomputed after a pending pick)
+            bool pscan = np > 0;
+            while (cnt < W) {
+              int qpos = -1;
+              for (int p = sp; p < L; p += 32) {
+                const int idx = p + lane;
+                const bool un = idx < L && !(qa[idx] & kCheckedBit);
+                const unsigned b = __ballot_sync(kFull, un);
+                if (b) { qpos = p + __ffs(b) - 1; break; }
+              }
+              const unsigned long long qkey = qpos >= 0 ? (qa[qpos] & kKeyMask) : ~0ull;
+              if (pscan) {
+                unsigned long long best = ~0ull;
+                for (int i = lane; i < np; i += 32) {
+                  const unsigned long long k = pend[i];
+                  if (!(k & kCheckedBit) && k < best) best = k;
+                }
+                unsigned long long mn = best;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  const unsigned long long other = __shfl_xor_sync(kFull, mn, o);
+                  mn = other < mn ? other : mn;
+                }
+                pk = mn;
+                pscan = false;
+              }
+              if (qpos < 0 && pk == ~0ull) break;
+              if (qkey <= pk) {
+                if (lane == 0) { qa[qpos] |= kCheckedBit; s_cid[cnt] = static_cast<int>(key_id(qkey)); }
+                sp = qpos + 1;
+              } else {
+                // keys are distinct: exactly one lane owns the pending minimum and marks it
+                for (int i = lane; i < np; i += 32) {
+                  if (pend[i] == pk) { pend[i] = pk | kCheckedBit; s_cid[cnt] = static_cast<int>(key_id(pk)); }
+                }
+                pk = ~0ull;
+                pscan = true;
+              }
+              ++cnt;
+              __syncwarp();
             }
-            __syncthreads();
-            if (dest < L) queue[dest] = key;
-            __syncthreads();
+            if (lane == 0) s_cursor = sp;
           }
-          // 4. drop the candidates into their holes
-          for (int i = tid; i < m; i += blockDim.x) {
-            const int f = pos[i] + i;
-            if (f < L) queue[f] = cs[i];
-          }
-          if (tid == 0 && p0 < s_pmin) s_pmin = p0;
+          if (lane == 0) s_ncur = cnt;
         }
-        // every thread has read m (the m > 0 path passed barriers since; m == 0 rewrites 0 with 0)
-        if (tid == 0) { s_ndist += static_cast<unsigned long long>(nfresh); s_nfresh = 0; s_nacc = 0; }
-        __syncthreads();  // counters reset + queue settled before the next round
+        __syncthreads();  // (1)
+        ncur = s_ncur;
+        ncont = s_ncont;
+        if (ncur == 0 && ncont == 0 && fifo_tail == fifo_head && n_issued == n_consumed) break;  // nothing left anywhere
+
+        if (ncur > 0 || ncont > 0) {
+          // -- A1: adjacency ids -> visited test-and-set -> ordered compaction of the fresh ids into the FIFO --
+          const bool cont_mode = ncur == 0;  // draining the CSR continuation of a row longer than kEll
+          long long e0 = 0;
+          int nslots = ncur * kEll;
+          if (cont_mode) {
+            e0 = s_cont_e[ncont - 1];
+            nslots = static_cast<int>(min(static_cast<long long>(kGsThreads), s_cont_end[ncont - 1] - e0));
+          }
+          int nb[kRounds];
+          unsigned bal[kRounds];
+          bool fr[kRounds];
+#pragma unroll
+          for (int r = 0; r < kRounds; ++r) {
+            const int s = r * kGsThreads + tid;
+            nb[r] = -1;
+            if (s < nslots)
+              nb[r] = cont_mode ? a.nbrs[e0 + s] : __ldg(a.ell + static_cast<int64_t>(s_cid[s >> 6]) * kEll + (s & (kEll - 1)));
+          }
+#pragma unroll
+          for (int r = 0; r < kRounds; ++r) {
+            fr[r] = false;
+            if (nb[r] >= 0) {
+              const uint32_t bit = 1u << (nb[r] & 31);
+              fr[r] = !(atomicOr(&visited[nb[r] >> 5], bit) & bit);  // ExpandOneCandidate :403-406
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < kRounds; ++r) {
+            bal[r] = __ballot_sync(kFull, fr[r]);
+            const unsigned vb = __ballot_sync(kFull, nb[r] >= 0);
+            if (lane == 0) { s_wcnt[r][warp] = __popc(bal[r]); st_nedge += static_cast<unsigned long long>(__popc(vb)); }
+          }
+          __syncthreads();  // (2)
+          int total = 0;
+#pragma unroll
+          for (int r = 0; r < kRounds; ++r) {
+            int mine = 0;
+#pragma unroll
+            for (int w = 0; w < kGsThreads / 32; ++w) {
+              if (w == warp) mine = total;
+              total += s_wcnt[r][w];
+            }
+            if (fr[r]) fifo[(fifo_tail + static_cast<uint32_t>(mine + __popc(bal[r] & lane_lt))) & (kFC - 1)] = nb[r];
+          }
+          fifo_tail += static_cast<uint32_t>(total);
+          if (cont_mode) {
+            if (tid == 0) {
+              s_cont_e[ncont - 1] = e0 + nslots;
+              if (e0 + nslots >= s_cont_end[ncont - 1]) s_ncont = ncont - 1;
+            }
+          } else {
+            // a full fixed-stride row may continue in the CSR (rare: repair hubs, reference graphs above 64)
+#pragma unroll
+            for (int r = 0; r < kRounds; ++r) {
+              const int s = r * kGsThreads + tid;
+              if (s < nslots && (s & (kEll - 1)) == kEll - 1 && nb[r] >= 0) {
+                const int c = s_cid[s >> 6];
+                const long long eb = a.offsets[c] + kEll, ee = a.offsets[c + 1];
+                if (ee > eb) {
+                  const int i = atomicAdd(&s_ncont, 1);
+                  s_cont_e[i] = eb;
+                  s_cont_end[i] = ee;
+                }
+              }
+            }
+            if (tid == 0) st_nexp += static_cast<unsigned long long>(ncur);
+          }
+          if (tid == 0) st_ndist += static_cast<unsigned long long>(total);
+        }
       }
-      const int pmin = s_pmin;
-      k = (pmin <= k) ? pmin : k + 1;  // :648-652 (only warp 0 consumes k)
+
+      // -- B: issue bulk copies of fresh rows into free ring slots;  C: consume landed rows --
+      // wide: C (rows issued one iteration ago, landed during A) then B;  exact: B then C of the same rows.
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) {
+        const bool do_issue = (phase == 0) == (a.exact != 0);
+        __syncthreads();  // FIFO / slot ids / pending appends of the previous phase are visible
+        if (do_issue) {
+          const uint32_t can = min(fifo_tail - fifo_head, static_cast<uint32_t>(R) - (n_issued - n_consumed));
+          if (warp == 0 && static_cast<uint32_t>(lane) < can) {
+            const uint32_t g = n_issued + lane, slot = g % static_cast<uint32_t>(R);
+            const int id = fifo[(fifo_head + lane) & (kFC - 1)];
+            slot_id[slot] = id;
+            if (staged) {
+              const uint32_t bar = bar0 + 8 * slot;
+              mbar_expect_tx(bar, row_bytes);
+              bulk_load_1d(ring0 + slot * static_cast<uint32_t>(a.slot_bytes), a.vectors + static_cast<int64_t>(id) * a.dim, row_bytes, bar);
+            }
+          }
+          n_issued += can;
+          fifo_head += can;
+        } else {
+          const unsigned long long bound = qa[L - 1] & kKeyMask;  // worst entry as of the last merge (:546)
+          for (uint32_t r = n_consumed + warp * 4 + team; r < n_issued; r += kGsThreads / 8) {
+            const uint32_t slot = r % static_cast<uint32_t>(R);
+            const int id = slot_id[slot];
+            float p;
+            if (staged) {
+              mbar_wait(bar0 + 8 * slot, (r / static_cast<uint32_t>(R)) & 1u);
+              const float4* row = reinterpret_cast<const float4*>(ring + static_cast<size_t>(slot) * a.slot_bytes);
+              p = a.metric == EPS_METRIC_L2 ? team_partial_vec4<true>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl)
+                                            : team_partial_vec4<false>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl);
+            } else {
+              const float* row = a.vectors + static_cast<int64_t>(id) * a.dim;
+              p = a.metric == EPS_METRIC_L2 ? team_partial_scalar<true>(row, qv, a.dim, tl) : team_partial_scalar<false>(row, qv, a.dim, tl);
+            }
+            p += __shfl_xor_sync(team_mask, p, 4);
+            p += __shfl_xor_sync(team_mask, p, 2);
+            p += __shfl_xor_sync(team_mask, p, 1);
+            if (tl == 0) {
+              const unsigned long long key = make_key(finish_metric(a.metric, p), static_cast<uint32_t>(id));
+              if (key < bound) pend[atomicAdd(&s_npend, 1)] = key;  // dist > bound rejected (:424); ties by id
+            }
+          }
+          n_consumed = n_issued;
+        }
+      }
+      if (a.exact) __syncthreads();  // (wide: the consume phase was already followed by a barrier)
+      // -- D: merge the pending keys (every iteration in exact mode; when the buffer could overflow otherwise) --
+      const int m = s_npend;
+      if (m > 0 && (a.exact || m > kPC - R)) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor);
     }
 
     // ---- results + visited reset (:711-714) ----
+    {
+      const int m = s_npend;  // only checked entries can be left (the last pick found nothing unchecked)
+      if (m > 0) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor);
+    }
     unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
-    for (int i = tid; i < L; i += blockDim.x) out[i] = queue[i];
+    for (int i = tid; i < L; i += kGsThreads) out[i] = qa[i];
     {
       uint4* v4 = reinterpret_cast<uint4*>(visited);
       const int64_t n4 = a.visited_words >> 2;
       const uint4 z = make_uint4(0, 0, 0, 0);
-      for (int64_t i = tid; i < n4; i += blockDim.x) v4[i] = z;
+      for (int64_t i = tid; i < n4; i += kGsThreads) v4[i] = z;
     }
-    if (tid == 0) s_ndist += static_cast<unsigned long long>(L);
   }
-  __syncthreads();
-  if (tid == 0) {
-    atomicAdd(&a.stats[0], s_ndist);
-    atomicAdd(&a.stats[1], s_nexp);
-    atomicAdd(&a.stats[2], s_nedge);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// v2 of the kernel: same algorithm and results, restructured against the two stalls the ncu capture of v1
-// showed (profiles/r01_ncu_graph_search_v1_*: barrier 8.4 and long_scoreboard 7.5 per issue, 16 % DRAM):
-//   * fixed-stride adjacency (kEll ids per vertex, -1 padded) => the neighbour ids are ONE load away from the
-//     vertex id (CSR needs offsets first); rows longer than kEll continue in the CSR (rare: repair hubs);
-//   * the adjacency row of the NEXT likely candidate (second unchecked entry) is loaded speculatively by the
-//     otherwise idle warps 2-3 while warps 0-1 run the visited test of the current one;
-//   * the seed distances arrive precomputed as a dense [B x L] tile product (the seed set is query-independent,
-//     SURVEY §8a A4) instead of L warp-per-row evaluations per query;
-//   * the merge shifts in place in super-tiles of 8 keys per thread (2 barriers per 1024 keys instead of per 128);
-//   * a lane issues all 128-bit loads of a row before the first use (one memory round trip per row).
-// Three barriers per expansion when nothing is accepted (the common case late in a search), six otherwise.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kEll = 64;
-
-struct GS2Args {
-  const float* vectors;
-  const int64_t* offsets;
-  const int32_t* nbrs;
-  const int32_t* ell;             // [n x kEll]
-  const int32_t* init_ids;
-  const float* seed_dist;         // [nq x seed_ld]
-  const float* queries;
-  uint32_t* visited;
-  unsigned long long* out_queue;
-  int* work_counter;
-  unsigned long long* stats;
-  int64_t visited_words;
-  int64_t seed_ld;
-  int dim, metric, vec4;
-  int L, Lp;
-  int nq;
-};
-
-__global__ void __launch_bounds__(128, 7) graph_search_kernel_v2(GS2Args a) {
-  extern __shared__ __align__(16) unsigned char gs_smem[];
-  unsigned long long* qa = reinterpret_cast<unsigned long long*>(gs_smem);  // [Lp] current queue
-  unsigned long long* cand = qa + a.Lp;                                     // [kCH]
-  unsigned long long* cs = cand + kCH;                                      // [kCH]
-  float* qv = reinterpret_cast<float*>(cs + kCH);                           // [dim4]
-  int* pos = reinterpret_cast<int*>(qv + ((a.dim + 3) & ~3));               // [kCH]
-  int* fresh = pos + kCH;                                                   // [kCH]
-  int* spec = fresh + kCH;                                                  // [2][kEll]
-  __shared__ int s_q, s_cur, s_nfresh, s_nacc, s_pmin, s_more;
-  __shared__ int s_spec_id[2];
-  __shared__ unsigned long long s_ndist, s_nexp, s_nedge;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  uint32_t* visited = a.visited + static_cast<int64_t>(blockIdx.x) * a.visited_words;
-  const int L = a.L;
-  if (tid == 0) { s_ndist = 0; s_nexp = 0; s_nedge = 0; }
-
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_q = atomicAdd(a.work_counter, 1);
-    __syncthreads();
-    const int q = s_q;
-    if (q >= a.nq) break;
-    for (int i = tid; i < a.dim; i += blockDim.x) qv[i] = a.queries[static_cast<int64_t>(q) * a.dim + i];
-    for (int i = tid; i < a.Lp; i += blockDim.x) {
-      unsigned long long key = kKeyInf;
-      if (i < L) {
-        const uint32_t id = static_cast<uint32_t>(a.init_ids[i]);
-        atomicOr(&visited[id >> 5], 1u << (id & 31));
-        key = make_key(a.seed_dist[static_cast<int64_t>(q) * a.seed_ld + i], id);
-      }
-      qa[i] = key;
-    }
-    if (tid == 0) { s_nfresh = 0; s_nacc = 0; s_spec_id[0] = -1; s_spec_id[1] = -1; }
-    __syncthreads();
-    block_bitonic_sort(qa, a.Lp);
-
-    int k = 0;
-    for (int it = 0;; ++it) {
-      const int par = it & 1;
-      if (warp == 0) {
-        int found = -1, next = -1;
-        for (int p = k; p < L; p += 32) {
-          const int idx = p + lane;
-          const bool un = idx < L && !(qa[idx] & kCheckedBit);
-          unsigned b = __ballot_sync(kFull, un);
-          if (found < 0 && b) { found = p + __ffs(b) - 1; b &= b - 1; }
-          if (found >= 0 && b) { next = p + __ffs(b) - 1; break; }
-          if (found >= 0 && p >= found + 96) break;  // bounded look-ahead for the speculation
-        }
-        if (lane == 0) {
-          s_cur = found;
-          s_pmin = L;
-          s_more = 0;
-          if (found >= 0) qa[found] |= kCheckedBit;
-          s_spec_id[par] = next >= 0 ? static_cast<int>(key_id(qa[next])) : -1;
-        }
-      }
-      __syncthreads();  // (1)
-      const int cur = s_cur;
-      if (cur < 0) break;
-      const int c = static_cast<int>(key_id(qa[cur]));
-      const bool hit = s_spec_id[par ^ 1] == c;
-      if (tid < kEll) {
-        const int nb = hit ? spec[(par ^ 1) * kEll + tid] : __ldg(a.ell + static_cast<int64_t>(c) * kEll + tid);
-        if (nb >= 0) {
-          const uint32_t bit = 1u << (nb & 31);
-          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
-          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = nb;
-          if (tid == kEll - 1) s_more = 1;  // full row: it may continue in the CSR
-        }
-        const unsigned vb = __ballot_sync(kFull, nb >= 0);
-        if (lane == 0 && vb) atomicAdd(&s_nedge, static_cast<unsigned long long>(__popc(vb)));
-      } else {
-        const int c2 = s_spec_id[par];
-        if (c2 >= 0) spec[par * kEll + (tid - kEll)] = __ldg(a.ell + static_cast<int64_t>(c2) * kEll + (tid - kEll));
-      }
-      __syncthreads();  // (2)
-      int64_t e_next = 0, e_end = 0;
-      if (s_more) { e_next = a.offsets[c] + kEll; e_end = a.offsets[c + 1]; }
-      if (tid == 0) { ++s_nexp; }
-      for (;;) {
-        const int nfresh = s_nfresh;
-        const unsigned long long bound = qa[L - 1] & kKeyMask;
-        for (int i = warp; i < nfresh; i += nwarps) {
-          const int nb = fresh[i];
-          float d = warp_distance(a.metric, a.vec4 != 0, a.vectors + static_cast<int64_t>(nb) * a.dim, qv, a.dim, lane);
-          if (lane == 0) {
-            const unsigned long long key = make_key(d, static_cast<uint32_t>(nb));
-            if (key < bound) cand[atomicAdd(&s_nacc, 1)] = key;
-          }
-        }
-        __syncthreads();  // (3)
-        const int m = s_nacc;
-        if (m > 0) {
-          for (int i = tid; i < m; i += blockDim.x) {
-            const unsigned long long key = cand[i];
-            int r = 0;
-            for (int j = 0; j < m; ++j) r += (cand[j] < key);
-            cs[r] = key;
-          }
-          __syncthreads();
-          for (int i = tid; i < m; i += blockDim.x) pos[i] = lb_masked(qa, L, cs[i]);
-          __syncthreads();
-          const int p0 = pos[0];
-          // in-place shift of [p0, L): super-tiles of 8 keys per thread, top first; each key moves right by
-          // the number of accepted candidates that precede it (counted linearly: m is small)
-          for (int hi = L; hi > p0; hi -= 8 * 128) {
-            unsigned long long kreg[8];
-            int dreg[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = hi - 1 - (u * 128 + tid);
-              dreg[u] = L;
-              if (j >= p0) {
-                kreg[u] = qa[j];
-                int sft = 0;
-                if (m <= 8) { for (int i = 0; i < m; ++i) sft += (pos[i] <= j); }
-                else { int lo = 0, up = m; while (lo < up) { const int mid = (lo + up) >> 1; if (pos[mid] <= j) lo = mid + 1; else up = mid; } sft = lo; }
-                dreg[u] = j + sft;
-              }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int u = 0; u < 8; ++u) if (dreg[u] < L) qa[dreg[u]] = kreg[u];
-            __syncthreads();
-          }
-          for (int i = tid; i < m; i += blockDim.x) {
-            const int f = pos[i] + i;
-            if (f < L) qa[f] = cs[i];
-          }
-          if (tid == 0 && p0 < s_pmin) s_pmin = p0;
-        }
-        if (tid == 0) { s_ndist += static_cast<unsigned long long>(nfresh); s_nfresh = 0; s_nacc = 0; }
-        __syncthreads();  // queue + counters settled
-        if (e_next >= e_end) break;
-        // rare: the row continues in the CSR beyond its first kEll entries
-        const int cnt = static_cast<int>(min(static_cast<int64_t>(kCH), e_end - e_next));
-        if (tid < cnt) {
-          const uint32_t nb = static_cast<uint32_t>(a.nbrs[e_next + tid]);
-          const uint32_t bit = 1u << (nb & 31);
-          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
-          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = static_cast<int>(nb);
-        }
-        e_next += cnt;
-        __syncthreads();
-      }
-      const int pmin = s_pmin;
-      k = (pmin <= k) ? pmin : k + 1;
-    }
-
-    unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
-    for (int i = tid; i < L; i += blockDim.x) out[i] = qa[i];
-    {
-      uint4* v4 = reinterpret_cast<uint4*>(visited);
-      const int64_t n4 = a.visited_words >> 2;
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      for (int64_t i = tid; i < n4; i += blockDim.x) v4[i] = z;
-    }
-    if (tid == 0) s_ndist += static_cast<unsigned long long>(L);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    atomicAdd(&a.stats[0], s_ndist);
-    atomicAdd(&a.stats[1], s_nexp);
-    atomicAdd(&a.stats[2], s_nedge);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Wide variant: W unchecked candidates are expanded per iteration (their neighbour rows are tested, gathered
-// and merged together).  This is the device analogue of the reference's IntraQueryThreads > 1 mode
-// (vec_search_executor.cpp:601-698: M candidates dealt to workers, expanded against a slightly stale bound,
-// merged back) — like that mode it is NOT bit-identical to the sequential order (W = 1, kernels above, is);
-// it trades that for W-fold fewer dependent round trips per query.  Same queue / visited / bound rules.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kWideMax = 8;
-constexpr int kWCap = kWideMax * kEll;  // fresh / candidate slots per iteration
-
-__global__ void __launch_bounds__(128, 7) graph_search_kernel_wide(GS2Args a, int W) {
-  extern __shared__ __align__(16) unsigned char gs_smem[];
-  unsigned long long* qa = reinterpret_cast<unsigned long long*>(gs_smem);  // [Lp]
-  unsigned long long* cand = qa + a.Lp;                                     // [kWCap]
-  unsigned long long* cs = cand + kWCap;                                    // [kWCap]
-  float* qv = reinterpret_cast<float*>(cs + kWCap);                         // [dim4]
-  int* pos = reinterpret_cast<int*>(qv + ((a.dim + 3) & ~3));               // [kWCap]
-  int* fresh = pos + kWCap;                                                 // [kWCap]
-  __shared__ int s_q, s_ncur, s_first, s_nfresh, s_nacc, s_pmin, s_more;
-  __shared__ int s_cid[kWideMax];
-  __shared__ unsigned long long s_ndist, s_nexp, s_nedge;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  uint32_t* visited = a.visited + static_cast<int64_t>(blockIdx.x) * a.visited_words;
-  const int L = a.L;
-  if (tid == 0) { s_ndist = 0; s_nexp = 0; s_nedge = 0; }
-
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_q = atomicAdd(a.work_counter, 1);
-    __syncthreads();
-    const int q = s_q;
-    if (q >= a.nq) break;
-    for (int i = tid; i < a.dim; i += blockDim.x) qv[i] = a.queries[static_cast<int64_t>(q) * a.dim + i];
-    for (int i = tid; i < a.Lp; i += blockDim.x) {
-      unsigned long long key = kKeyInf;
-      if (i < L) {
-        const uint32_t id = static_cast<uint32_t>(a.init_ids[i]);
-        atomicOr(&visited[id >> 5], 1u << (id & 31));
-        key = make_key(a.seed_dist[static_cast<int64_t>(q) * a.seed_ld + i], id);
-      }
-      qa[i] = key;
-    }
-    if (tid == 0) { s_nfresh = 0; s_nacc = 0; }
-    __syncthreads();
-    block_bitonic_sort(qa, a.Lp);
-
-    int k = 0;
-    for (;;) {
-      if (warp == 0) {
-        int cnt = 0, first = -1;
-        for (int p = k; p < L && cnt < W; p += 32) {
-          const int idx = p + lane;
-          const bool un = idx < L && !(qa[idx] & kCheckedBit);
-          unsigned b = __ballot_sync(kFull, un);
-          while (b && cnt < W) {
-            const int at = p + __ffs(b) - 1;
-            if (first < 0) first = at;
-            if (lane == 0) { s_cid[cnt] = static_cast<int>(key_id(qa[at])); qa[at] |= kCheckedBit; }
-            b &= b - 1;
-            ++cnt;
-          }
-        }
-        if (lane == 0) { s_ncur = cnt; s_first = first; s_pmin = L; s_more = 0; }
-      }
-      __syncthreads();  // (1)
-      const int ncur = s_ncur;
-      if (ncur == 0) break;
-      for (int slot = tid; slot < ncur * kEll; slot += blockDim.x) {
-        const int ci = slot / kEll, e = slot % kEll;
-        const int nb = __ldg(a.ell + static_cast<int64_t>(s_cid[ci]) * kEll + e);
-        if (nb >= 0) {
-          const uint32_t bit = 1u << (nb & 31);
-          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
-          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = nb;
-          if (e == kEll - 1) atomicOr(&s_more, 1 << ci);
-        }
-        const unsigned vb = __ballot_sync(kFull, nb >= 0);  // ncur * kEll is a multiple of 32: warp-uniform trip count
-        if (lane == 0 && vb) atomicAdd(&s_nedge, static_cast<unsigned long long>(__popc(vb)));
-      }
-      __syncthreads();  // (2)
-      if (tid == 0) s_nexp += static_cast<unsigned long long>(ncur);
-      const int more = s_more;
-      int over_ci = -1;  // candidate whose CSR continuation is being drained (rare: rows longer than kEll)
-      int64_t e_next = 0, e_end = 0;
-      for (;;) {
-        const int nfresh = s_nfresh;
-        const unsigned long long bound = qa[L - 1] & kKeyMask;
-        for (int i = warp; i < nfresh; i += nwarps) {
-          const int nb = fresh[i];
-          float d = warp_distance(a.metric, a.vec4 != 0, a.vectors + static_cast<int64_t>(nb) * a.dim, qv, a.dim, lane);
-          if (lane == 0) {
-            const unsigned long long key = make_key(d, static_cast<uint32_t>(nb));
-            if (key < bound) cand[atomicAdd(&s_nacc, 1)] = key;
-          }
-        }
-        __syncthreads();  // (3)
-        const int m = s_nacc;
-        if (m > 0) {
-          for (int i = tid; i < m; i += blockDim.x) {
-            const unsigned long long key = cand[i];
-            int r = 0;
-            for (int j = 0; j < m; ++j) r += (cand[j] < key);
-            cs[r] = key;
-          }
-          __syncthreads();
-          for (int i = tid; i < m; i += blockDim.x) pos[i] = lb_masked(qa, L, cs[i]);
-          __syncthreads();
-          const int p0 = pos[0];
-          for (int hi = L; hi > p0; hi -= 8 * 128) {
-            unsigned long long kreg[8];
-            int dreg[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = hi - 1 - (u * 128 + tid);
-              dreg[u] = L;
-              if (j >= p0) {
-                kreg[u] = qa[j];
-                int sft = 0;
-                if (m <= 8) { for (int i = 0; i < m; ++i) sft += (pos[i] <= j); }
-                else { int lo = 0, up = m; while (lo < up) { const int mid = (lo + up) >> 1; if (pos[mid] <= j) lo = mid + 1; else up = mid; } sft = lo; }
-                dreg[u] = j + sft;
-              }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int u = 0; u < 8; ++u) if (dreg[u] < L) qa[dreg[u]] = kreg[u];
-            __syncthreads();
-          }
-          for (int i = tid; i < m; i += blockDim.x) {
-            const int f = pos[i] + i;
-            if (f < L) qa[f] = cs[i];
-          }
-          if (tid == 0 && p0 < s_pmin) s_pmin = p0;
-        }
-        if (tid == 0) { s_ndist += static_cast<unsigned long long>(nfresh); s_nfresh = 0; s_nacc = 0; }
-        __syncthreads();
-        // next CSR continuation chunk, if any candidate's row exceeded the fixed stride
-        while (e_next >= e_end) {
-          ++over_ci;
-          while (over_ci < ncur && !((more >> over_ci) & 1)) ++over_ci;
-          if (over_ci >= ncur) break;
-          e_next = a.offsets[s_cid[over_ci]] + kEll;
-          e_end = a.offsets[s_cid[over_ci] + 1];
-        }
-        if (over_ci >= ncur) break;
-        const int cnt = static_cast<int>(min(static_cast<int64_t>(kEll), e_end - e_next));
-        if (tid < cnt) {
-          const uint32_t nb = static_cast<uint32_t>(a.nbrs[e_next + tid]);
-          const uint32_t bit = 1u << (nb & 31);
-          const uint32_t old = atomicOr(&visited[nb >> 5], bit);
-          if (!(old & bit)) fresh[atomicAdd(&s_nfresh, 1)] = static_cast<int>(nb);
-        }
-        e_next += cnt;
-        __syncthreads();
-      }
-      const int pmin = s_pmin, first = s_first;
-      k = pmin < first + 1 ? pmin : first + 1;
-    }
-
-    unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
-    for (int i = tid; i < L; i += blockDim.x) out[i] = qa[i];
-    {
-      uint4* v4 = reinterpret_cast<uint4*>(visited);
-      const int64_t n4 = a.visited_words >> 2;
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      for (int64_t i = tid; i < n4; i += blockDim.x) v4[i] = z;
-    }
-    if (tid == 0) s_ndist += static_cast<unsigned long long>(L);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    atomicAdd(&a.stats[0], s_ndist);
-    atomicAdd(&a.stats[1], s_nexp);
-    atomicAdd(&a.stats[2], s_nedge);
-  }
+  if (st_ndist) atomicAdd(&a.stats[0], st_ndist);
+  if (st_nexp) atomicAdd(&a.stats[1], st_nexp);
+  if (st_nedge) atomicAdd(&a.stats[2], st_nedge);
 }
 
 __global__ void csr_to_ell_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbrs, int64_t n,
@@ -638,32 +493,40 @@ int prepare_init_ids(Index* ix, int64_t L) {
   return EPS_OK;
 }
 
+
+// Ring geometry: ~48 KB of row slots per CTA (16 rows at d = 768), at least 2, at most kMaxR slots.
+// EPS_GRAPH_RING (developer knob, read once) overrides the slot count.
+static int ring_slots_for(int slot_bytes) {
+  static const int env_slots = [] { const char* e = getenv("EPS_GRAPH_RING"); return e ? atoi(e) : 0; }();
+  if (slot_bytes <= 0) return 16;
+  int r = env_slots > 0 ? env_slots : (48 * 1024) / slot_bytes;
+  return std::max(2, std::min(r, kMaxR));
+}
+
 int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsigned long long* d_queue,
                  eps_stats* stats) {
   if (L < 1 || L > ix->n_indexed) return fail(EPS_ERR_INVALID_ARGUMENT, "graph_search: L out of range");
-  const int Lp = next_pow2(static_cast<int>(L));
+  const int Lp = std::max(2, next_pow2(static_cast<int>(L)));
   if (Lp > 16384) return fail(EPS_ERR_UNSUPPORTED, "SearchQueueSize above 16384 is not supported by the graph kernel");
   EPS_TRY(prepare_init_ids(ix, L));
-  const int dimp = (static_cast<int>(ix->dim) + 3) & ~3;
-  const bool use_v2 = getenv("EPS_GRAPH_V1") == nullptr;
-  const int width = use_v2 ? std::max(1, std::min(ix->search_width, kWideMax)) : 1;
-  const size_t smem = width > 1 ? static_cast<size_t>(Lp) * 8 + 2 * kWCap * 8 + static_cast<size_t>(dimp) * 4 + 2 * kWCap * 4
-                      : use_v2 ? static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4 + 2 * kEll * 4
-                             : static_cast<size_t>(Lp) * 8 + 2 * kCH * 8 + static_cast<size_t>(dimp) * 4 + 2 * kCH * 4;
-  if (smem > 220 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query do not fit in shared memory");
+  const int dim = static_cast<int>(ix->dim);
+  const int dimp = (dim + 3) & ~3;
+  const int width = std::max(1, std::min(ix->search_width, kMaxW));
+  const bool staged = ix->vec4;  // 16-byte aligned rows of a multiple of 16 bytes: eligible for bulk async copies
+  const int slot_bytes = staged ? dim * 4 : 0;
+  int R = ring_slots_for(slot_bytes);
+  auto smem_for = [&](int r) {
+    return static_cast<size_t>(r) * slot_bytes + static_cast<size_t>(Lp) * 8 + 2 * kPC * 8 + kMaxR * 8 +
+           static_cast<size_t>(dimp) * 4 + kPC * 4 + kFC * 4 + kMaxR * 4;
+  };
+  while (R > 2 && smem_for(R) > 200 * 1024) --R;
+  const size_t smem = smem_for(R);
+  if (smem > 226 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query + row ring do not fit in shared memory");
   int per_sm = 0;
-  if (width > 1) {
-    EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel_wide, 128, smem));
-  } else if (use_v2) {
-    EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel_v2, 128, smem));
-  } else {
-    EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel, 128, smem));
-  }
+  EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel, kGsThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  int slots = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(per_sm) * ix->num_sms));
+  const int slots = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(per_sm) * ix->num_sms));
   const int64_t words = ((ix->n_indexed + 31) / 32 + 3) & ~3ll;
   if (ix->visited_slots < slots || ix->s_visited.cap < static_cast<size_t>(slots) * words * 4) {
     EPS_TRY(ix->s_visited.reserve(static_cast<size_t>(slots) * words * 4));
@@ -678,46 +541,37 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   EPS_TRY(ix->s_misc.reserve(64));
   EPS_CUDA(cudaMemsetAsync(ix->s_misc.p, 0, 64, ix->stream));
   uint64_t launches = 1;
-  if (use_v2) {
-    if (!ix->d_ell) {  // fixed-stride adjacency, built once per installed graph
-      EPS_CUDA(cudaMalloc(&ix->d_ell, static_cast<size_t>(ix->n_indexed) * kEll * 4));
-      const int64_t tot = ix->n_indexed * kEll;
-      csr_to_ell_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(ix->d_offsets, ix->d_nbrs,
-                                                                                          ix->n_indexed, ix->d_ell);
-      EPS_CUDA(cudaGetLastError());
-    }
-    if (ix->seed_rows_L != L) {  // contiguous copy of the query-independent seed rows
-      EPS_TRY(ix->s_seed_rows.reserve(static_cast<size_t>(L) * ix->dim * 4));
-      const int64_t tot = L * ix->dim;
-      gather_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(
-          ix->d_vectors, ix->d_init_ids, static_cast<int>(L), static_cast<int>(ix->dim), ix->s_seed_rows.as<float>());
-      EPS_CUDA(cudaGetLastError());
-      ix->seed_rows_L = L;
-    }
-    const int64_t seed_ld = (L + 3) & ~3ll;
-    EPS_TRY(ix->s_seed_dist.reserve(static_cast<size_t>(nq) * seed_ld * 4));
-    EPS_TRY(launch_distances(ix, ix->s_seed_rows.as<float>(), 0, L, d_queries, nq, ix->s_seed_dist.as<float>(), seed_ld,
-                             &launches));
-    GS2Args a;
-    a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.ell = ix->d_ell;
-    a.init_ids = ix->d_init_ids; a.seed_dist = ix->s_seed_dist.as<float>(); a.queries = d_queries;
-    a.visited = ix->s_visited.as<uint32_t>(); a.out_queue = d_queue;
-    a.work_counter = reinterpret_cast<int*>(ix->s_misc.as<unsigned char>() + 32);
-    a.stats = ix->s_misc.as<unsigned long long>();
-    a.visited_words = words; a.seed_ld = seed_ld; a.dim = static_cast<int>(ix->dim); a.metric = ix->metric;
-    a.vec4 = ix->vec4 ? 1 : 0; a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
-    if (width > 1) graph_search_kernel_wide<<<slots, 128, smem, ix->stream>>>(a, width);
-    else graph_search_kernel_v2<<<slots, 128, smem, ix->stream>>>(a);
-  } else {
-    GSArgs a;
-    a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.init_ids = ix->d_init_ids;
-    a.queries = d_queries; a.visited = ix->s_visited.as<uint32_t>(); a.out_queue = d_queue;
-    a.work_counter = reinterpret_cast<int*>(ix->s_misc.as<unsigned char>() + 32);
-    a.stats = ix->s_misc.as<unsigned long long>();
-    a.visited_words = words; a.dim = static_cast<int>(ix->dim); a.metric = ix->metric; a.vec4 = ix->vec4 ? 1 : 0;
-    a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
-    graph_search_kernel<<<slots, 128, smem, ix->stream>>>(a);
+  if (!ix->d_ell) {  // fixed-stride adjacency, built once per installed graph
+    EPS_CUDA(cudaMalloc(&ix->d_ell, static_cast<size_t>(ix->n_indexed) * kEll * 4));
+    const int64_t tot = ix->n_indexed * kEll;
+    csr_to_ell_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(ix->d_offsets, ix->d_nbrs,
+                                                                                        ix->n_indexed, ix->d_ell);
+    EPS_CUDA(cudaGetLastError());
+    ++launches;
   }
+  if (ix->seed_rows_L != L) {  // contiguous copy of the query-independent seed rows
+    EPS_TRY(ix->s_seed_rows.reserve(static_cast<size_t>(L) * ix->dim * 4));
+    const int64_t tot = L * ix->dim;
+    gather_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(
+        ix->d_vectors, ix->d_init_ids, static_cast<int>(L), dim, ix->s_seed_rows.as<float>());
+    EPS_CUDA(cudaGetLastError());
+    ix->seed_rows_L = L;
+    ++launches;
+  }
+  const int64_t seed_ld = (L + 3) & ~3ll;
+  EPS_TRY(ix->s_seed_dist.reserve(static_cast<size_t>(nq) * seed_ld * 4));
+  EPS_TRY(launch_distances(ix, ix->s_seed_rows.as<float>(), 0, L, d_queries, nq, ix->s_seed_dist.as<float>(), seed_ld,
+                           &launches));
+  GSArgs a;
+  a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.ell = ix->d_ell;
+  a.init_ids = ix->d_init_ids; a.seed_dist = ix->s_seed_dist.as<float>(); a.queries = d_queries;
+  a.visited = ix->s_visited.as<uint32_t>(); a.out_queue = d_queue;
+  a.work_counter = reinterpret_cast<int*>(ix->s_misc.as<unsigned char>() + 32);
+  a.stats = ix->s_misc.as<unsigned long long>();
+  a.visited_words = words; a.seed_ld = seed_ld; a.dim = dim; a.metric = ix->metric;
+  a.vec4 = ix->vec4 ? 1 : 0; a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
+  a.W = width; a.exact = width == 1 ? 1 : 0; a.R = R; a.slot_bytes = slot_bytes;
+  graph_search_kernel<<<slots, kGsThreads, smem, ix->stream>>>(a);
   EPS_CUDA(cudaGetLastError());
   if (stats) {
     stats->n_seed += static_cast<uint64_t>(nq) * static_cast<uint64_t>(L);

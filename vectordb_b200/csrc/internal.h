@@ -14,6 +14,10 @@ namespace eps {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }  // error paths (EPS_TRY / EPS_CUDA early returns) must not leak device memory
   int reserve(size_t bytes);
   void release();
   template <typename T>

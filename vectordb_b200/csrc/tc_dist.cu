@@ -21,6 +21,7 @@
 
 #include <cstdlib>
 
+#include "async.cuh"
 #include "internal.h"
 
 namespace eps {
@@ -64,29 +65,6 @@ struct TcArgs {
                       // gain), 2 = experimental branch-light compare (epi_chunk_fast); 0 / unset = the validated default
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -256,7 +234,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int t = 0; t < 2; ++t) { mbar_init(tfull0 + 8 * t, 1); mbar_init(tempty0 + 8 * t, 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {  // TMEM: all 512 columns (two 256-column fp32 accumulators)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -466,7 +444,7 @@ tc_dist_kernel_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTc2Stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int t = 0; t < 2; ++t) { mbar_init(tfull0 + 8 * t, 1); mbar_init(tempty0 + 8 * t, 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
     const float qn = (a.metric == EPS_METRIC_L2 && i < a.nq) ? a.qnorm[i] : 0.f;
