@@ -142,6 +142,12 @@ EPS_API int eps_index_config(eps_index* ix, int64_t L_master, int64_t L_local, i
  * bound — higher throughput, results not bit-identical to the sequential order (as in the reference). */
 EPS_API int eps_index_set_search_width(eps_index* ix, int width);
 
+/* Launch geometry of the graph-search kernel (performance knob, never changes results in width 1 and only the
+ * usual run-to-run variation of the wide mode otherwise): ring_slots = shared-memory row slots per CTA that TMA
+ * bulk copies land in (0 = auto: ~48 KB of rows), ctas_per_sm = cap on resident CTAs, i.e. in-flight queries, per SM
+ * (0 = whatever fits).  No reference counterpart (the CPU executor has no such geometry). */
+EPS_API int eps_index_set_graph_tuning(eps_index* ix, int ring_slots, int ctas_per_sm);
+
 /* Precision of the COARSE pass of large-batch exact scans (nq >= 64): 0 = none (fp32 SIMT tiles only),
  * 1 = tcgen05 kind::tf32 on the fp32 rows (default), 2 = tcgen05 kind::f16 on a bf16 mirror of the table
  * (+50 % HBM).  Whatever the mode, the k + max(32, k) best coarse candidates of every query are re-evaluated

@@ -29,3 +29,9 @@ def golden():
 def have_ref():
     from oracle import oracle
     return oracle.have_ref()
+
+
+@pytest.fixture(scope="session")
+def golden_refgraph():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "refgraph20k.npz"), allow_pickle=False)

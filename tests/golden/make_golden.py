@@ -9,6 +9,10 @@ Fixtures
   halfcircle.npz    engine/test/engine/db/db_server.cpp:1085-1245 (QueryDenseVectorDuringRebuild, graph-path golden)
   rand2k.npz        seeded random table with a reference-built graph: search / filter / delete / tail / prefilter
                     outputs of VecSearchExecutor::Search at IntraQueryThreads = 1.
+  refgraph20k.npz   20 000 x 128 clustered table (tests/helpers.gen seed 901): the graph the REFERENCE builds on it
+                    (ANNGraphSegment::BuildFromVectorTable, 7 OpenMP threads) and what the reference's search
+                    gets on that graph at IntraQueryThreads 1 and 4 (recall@10, distance evaluations, result ids) —
+                    the yard-stick for the device build's quality and for the wide search mode.
 """
 import os
 import sys
@@ -163,10 +167,41 @@ def rand2k():
     np.savez_compressed(os.path.join(OUT, "rand2k.npz"), **out)
 
 
+def refgraph20k():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import exact_topk, gen, recall
+    n, d, nq = 20000, 128, 128
+    X, Q = gen(n, d, 901, "cluster"), gen(nq, d, 902, "cluster")
+    truth = exact_topk(X, Q, 10)
+    r = Ref("l2", d, n, [("ID", "int4")])
+    r.set_rows(X)
+    n_idx, off, nb, nav = r.build(n, threads=7)
+    out = {"offsets": off.astype(np.int32), "nbrs": nb.astype(np.int32), "nav": np.int64(nav), "truth": truth.astype(np.int32),
+           "n": np.int64(n), "d": np.int64(d), "nq": np.int64(nq)}
+    for T in (1, 4):
+        for L in (64, 200, 500):
+            r.make_executors(1, T, L, counting=True)
+            ids = np.full((nq, 10), -1, np.int64)
+            ds = np.full((nq, 10), np.inf, np.float64)
+            nd = np.zeros(nq, np.int64)
+            for qi in range(nq):
+                a, b, c = r.search(Q[qi], 10)
+                ids[qi, :len(a)] = a
+                ds[qi, :len(a)] = b
+                nd[qi] = c
+            out["T%d_L%d_ids" % (T, L)] = ids.astype(np.int32)
+            out["T%d_L%d_dists" % (T, L)] = ds
+            out["T%d_L%d_ndist" % (T, L)] = nd
+            out["T%d_L%d_recall" % (T, L)] = np.float64(recall(ids, truth, 10))
+            print("refgraph20k T=%d L=%d recall %.4f n_dist %.0f" % (T, L, recall(ids, truth, 10), nd.mean()))
+    np.savez_compressed(os.path.join(OUT, "refgraph20k.npz"), **out)
+
+
 if __name__ == "__main__":
-    dense_vector()
-    halfcircle()
-    rand2k()
+    only = sys.argv[1:]
+    for fn in (dense_vector, halfcircle, rand2k, refgraph20k):
+        if not only or fn.__name__ in only:
+            fn()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -316,8 +316,9 @@ def test_exact_scan_adversarial_row_order_falls_back(vdb):
 
 
 def test_wide_expansion_matches_sequential_quality(vdb, port):
-    """expand width 2/4 = the analogue of the reference's IntraQueryThreads > 1: not bit-identical to the
-    sequential order, but the same answers on (almost) every query — like the reference's own T=4 vs T=1."""
+    """Search width 2/4/8 = the analogue of the reference's IntraQueryThreads > 1 (candidates expanded while the rows
+    of earlier ones are in flight): not bit-identical to the sequential order, but the same recall, nearly the same
+    answers and a bounded amount of extra work; width 1 stays deterministic."""
     n, d, nq = 20000, 64, 64
     X, Q = gen(n, d, 401, "cluster"), gen(nq, d, 402, "cluster")
     ix = vdb.Index("l2", d, host_vectors=X)
@@ -325,18 +326,119 @@ def test_wide_expansion_matches_sequential_quality(vdb, port):
     ix.build(n)
     ix.config(256, 256)
     truth = exact_topk(X, Q, 10)
+    ix.set_search_width(1)
     base, bd, _, st1 = ix.search(Q, 10)
     r1 = recall(base, truth, 10)
-    for w in (2, 4):
+    for w in (2, 4, 8):
         ix.set_search_width(w)
         ids, ds, cnt, st = ix.search(Q, 10)
         assert np.all(cnt == 10) and np.all(np.diff(ds, axis=1) >= 0)
         assert recall(ids, truth, 10) >= r1 - 0.01
-        assert (ids == base).mean() > 0.97
+        overlap = np.mean([len(set(ids[i]) & set(base[i])) / 10 for i in range(nq)])
+        assert overlap > 0.93, (w, overlap)
         assert st["n_dist"] <= 1.3 * st1["n_dist"]
     ix.set_search_width(1)
     again, _, _, _ = ix.search(Q, 10)
     assert np.array_equal(again, base)
+    ix.close()
+
+
+def test_search_on_reference_built_graph_20k(vdb, golden_refgraph):
+    """The reference's own graph (ANNGraphSegment::BuildFromVectorTable on 20 000 x 128, fixture refgraph20k) searched
+    on the device: width 1 against the reference at IntraQueryThreads = 1 (ids, distances, distance-evaluation
+    counts), width 4 against the reference at its default IntraQueryThreads = 4 (recall and work; that mode is racy
+    in the reference itself, so ids are compared as quality)."""
+    g = golden_refgraph
+    n, d, nq = int(g["n"]), int(g["d"]), int(g["nq"])
+    X, Q = gen(n, d, 901, "cluster"), gen(nq, d, 902, "cluster")
+    truth = g["truth"]
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.set_graph(n, g["offsets"].astype(np.int64), g["nbrs"].astype(np.int64), int(g["nav"]))
+    for L in (64, 200, 500):
+        ix.config(L, L)
+        ix.set_search_width(1)
+        ids, ds, cnt, st = ix.search(Q, 10)
+        want = g["T1_L%d_ids" % L].astype(np.int64)
+        rate = assert_same_results(ids, ds, cnt, want, g["T1_L%d_dists" % L], np.full(nq, 10), "refgraph L=%d" % L)
+        assert rate > 0.9
+        ref_nd = int(g["T1_L%d_ndist" % L].sum())
+        assert abs(st["n_dist"] - ref_nd) <= 0.02 * ref_nd, (L, st["n_dist"], ref_nd)
+        ix.set_search_width(4)
+        ids4, _, _, st4 = ix.search(Q, 10)
+        assert recall(ids4, truth, 10) >= float(g["T4_L%d_recall" % L]) - 0.02
+        assert st4["n_dist"] <= 1.3 * int(g["T4_L%d_ndist" % L].sum())
+    ix.close()
+
+
+@pytest.mark.parametrize("m", METRICS)
+def test_nn_descent_build_quality(vdb, m):
+    """B1: force the NN-descent branch (exact_knn_below far under n) and compare the searches on its graph with the
+    searches on the exact-kNN graph of the same rows: recall within 0.03 at equal L, at most 1.5x the distance
+    evaluations; the repair must not grow hubs."""
+    n, d, nq = 60000, 64, 128
+    X, Q = gen(n, d, 911, "cluster"), gen(nq, d, 912, "cluster")
+    if m == "cosine":
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    truth = exact_topk(X, Q, 10, m)
+    ix = vdb.Index(m, d, host_vectors=X)
+    ix.sync_rows(n)
+    res = {}
+    for name, below in (("exact", 100000), ("nnd", 1000)):
+        ix.build(n, exact_knn_below=below, knn_k=64)
+        ni, off, nb, nav = ix.get_graph()
+        deg = np.diff(off)
+        assert ni == n and deg.min() >= 1 and deg.max() <= 4 * 50, (name, deg.max())
+        ix.config(200, 200)
+        ix.set_search_width(1)
+        ids, _, _, st = ix.search(Q, 10)
+        res[name] = (recall(ids, truth, 10), st["n_dist"] / nq)
+    assert res["nnd"][0] >= res["exact"][0] - 0.03, res
+    assert res["nnd"][1] <= 1.5 * res["exact"][1], res
+    ix.close()
+
+
+def test_nn_descent_build_vs_reference_graph(vdb, golden_refgraph):
+    """The device build (NN-descent forced) on the fixture's 20 000 x 128 rows against the graph the reference built
+    on the same rows: recall at equal L within 0.03 of the reference's, distance evaluations at most 1.5x."""
+    g = golden_refgraph
+    n, d, nq = int(g["n"]), int(g["d"]), int(g["nq"])
+    X, Q = gen(n, d, 901, "cluster"), gen(nq, d, 902, "cluster")
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.build(n, exact_knn_below=1000)
+    ix.set_search_width(1)
+    for L in (200, 500):
+        ix.config(L, L)
+        ids, _, _, st = ix.search(Q, 10)
+        assert recall(ids, g["truth"], 10) >= float(g["T1_L%d_recall" % L]) - 0.03, L
+        assert st["n_dist"] <= 1.5 * int(g["T1_L%d_ndist" % L].sum()), L
+    ix.close()
+
+
+def test_build_repair_does_not_grow_hubs(vdb):
+    """B2 connectivity repair (nsg.cpp:734-775: nearest linked vertex of a search pool, else a random linked one) on
+    the case that used to produce one vertex of degree O(n): an inner-product field over positive data."""
+    n, d = 200000, 32
+    X = gen(n, d, 921)
+    ix = vdb.Index("ip", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.build(n, knn_k=64, nnd_iters=8)
+    ni, off, nb, nav = ix.get_graph()
+    deg = np.diff(off)
+    assert deg.max() <= 4 * 50, deg.max()
+    # every vertex reachable from the navigation point
+    seen = np.zeros(n, bool)
+    seen[nav] = True
+    frontier = np.array([nav])
+    while len(frontier):
+        nxt = np.unique(np.concatenate([nb[off[v]:off[v + 1]] for v in frontier])) if len(frontier) < 50000 else \
+            np.unique(nb[np.concatenate([np.arange(off[v], off[v + 1]) for v in frontier])])
+        nxt = nxt[~seen[nxt]]
+        seen[nxt] = True
+        frontier = nxt
+    assert seen.all()
     ix.close()
 
 

@@ -188,3 +188,20 @@ def test_search_is_deterministic_and_L_monotone(port, golden):
     c = port.search_batch(L=512, **kw)
     assert c[3][0] >= a[3][0]
     assert np.all(c[1][:, 0] <= a[1][:, 0] + 1e-12)  # the best distance can only improve with a longer queue
+
+
+def test_port_matches_reference_on_its_own_20k_graph(port, golden_refgraph):
+    """The C restatement on the graph the reference built over 20 000 x 128 rows (fixture refgraph20k, outputs of the
+    reference at IntraQueryThreads = 1): identical ids, distances and distance-evaluation counts."""
+    from helpers import assert_same_results, gen
+    g = golden_refgraph
+    n, d, nq = int(g["n"]), int(g["d"]), 32
+    X, Q = gen(n, d, 901, "cluster"), gen(int(g["nq"]), d, 902, "cluster")[:nq]
+    for L in (64, 200):
+        ids, ds, cnt, (nd, _) = port.search_batch(metric="l2", vectors=X, queries=Q, limit=10, n_indexed=n,
+                                                  offsets=g["offsets"].astype(np.int64), nbrs=g["nbrs"].astype(np.int64),
+                                                  nav=int(g["nav"]), L=L)
+        rate = assert_same_results(ids, ds, cnt, g["T1_L%d_ids" % L][:nq].astype(np.int64), g["T1_L%d_dists" % L][:nq],
+                                   np.full(nq, 10), "port on refgraph L=%d" % L)
+        assert rate == 1.0
+        assert nd == int(g["T1_L%d_ndist" % L][:nq].sum())

@@ -32,10 +32,13 @@ print("build: %.2f s" % (time.perf_counter() - t0))
 n, off, nb, nav = ix.get_graph()
 deg = np.diff(off)
 print("edges %d avg deg %.1f max %d nav %d" % (off[-1], deg.mean(), deg.max(), nav))
+tunes = [tuple(int(y) for y in x.split("x")) for x in os.environ.get("TUNES", "0x0").split(",")]  # ring x ctas
 for L in Ls:
-  for W in [int(x) for x in os.environ.get('WIDTHS', '1').split(',')]:
+ for W in [int(x) for x in os.environ.get('WIDTHS', '1').split(',')]:
+  for (ring, ctas) in tunes:
     ix.config(L, L)
     ix.set_search_width(W)
+    ix.set_graph_tuning(ring, ctas)
     for rep in range(2):
         st = ix.search_device(Q.data_ptr(), nq, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), want_stats=True)
     g = oi.cpu().numpy()
@@ -43,6 +46,6 @@ for L in Ls:
     nd, ns = st["n_dist"], st["n_seed"]
     byt = (nd - ns) * dim * 4 + st["n_edges"] * 4 + st["n_expand"] * 16 + L * dim * 4 + nq * (dim * 4 + k * 12)
     gbs = byt / (st["kernel_ms"] / 1e3) / 1e9
-    print(json.dumps({"L": L, "W": W, "recall": round(float(rec), 4), "n_dist_per_q": nd / nq, "n_expand_per_q": st["n_expand"] / nq,
+    print(json.dumps({"L": L, "W": W, "ring": ring, "ctas": ctas, "recall": round(float(rec), 4), "n_dist_per_q": nd / nq, "n_expand_per_q": st["n_expand"] / nq,
                       "kernel_ms": round(st["kernel_ms"], 3), "qps": round(nq / (st["kernel_ms"] / 1e3)), "GBps": round(gbs, 1),
                       "frac_of_6487": round(gbs / 6487.1, 3)}))

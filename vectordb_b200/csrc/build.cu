@@ -205,6 +205,26 @@ static int prune_pass(Index* ix, int64_t n, const unsigned long long* d_knn, int
   return EPS_OK;
 }
 
+// Install a host CSR (int64 offsets, int32 ids) as the index's graph, dropping everything derived from the old one.
+static int install_csr(Index* ix, int64_t n, const int64_t* off, const int32_t* nb, int64_t e, int64_t nav) {
+  if (ix->d_offsets) { cudaFree(ix->d_offsets); ix->d_offsets = nullptr; }
+  if (ix->d_nbrs) { cudaFree(ix->d_nbrs); ix->d_nbrs = nullptr; }
+  if (ix->d_init_ids) { cudaFree(ix->d_init_ids); ix->d_init_ids = nullptr; }
+  if (ix->d_ell) { cudaFree(ix->d_ell); ix->d_ell = nullptr; }
+  ix->seed_rows_L = 0;
+  ix->init_L = 0;
+  ix->n_indexed = 0;
+  EPS_CUDA(cudaMalloc(&ix->d_offsets, (static_cast<size_t>(n) + 1) * 8));
+  EPS_CUDA(cudaMalloc(&ix->d_nbrs, std::max<size_t>(static_cast<size_t>(e), 1) * 4));
+  EPS_CUDA(cudaMemcpyAsync(ix->d_offsets, off, (static_cast<size_t>(n) + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
+  if (e > 0) EPS_CUDA(cudaMemcpyAsync(ix->d_nbrs, nb, static_cast<size_t>(e) * 4, cudaMemcpyHostToDevice, ix->stream));
+  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->n_indexed = n;
+  ix->n_edges = e;
+  ix->nav = nav;
+  return EPS_OK;
+}
+
 int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
   eps_build_params bp;
   std::memset(&bp, 0, sizeof(bp));
@@ -297,12 +317,15 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
   std::vector<int32_t> h_ids(static_cast<size_t>(n) * stride), h_cnt(static_cast<size_t>(n));
   EPS_CUDA(cudaMemcpyAsync(h_ids.data(), ids2.p, h_ids.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
   EPS_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt2.p, h_cnt.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
-  std::vector<unsigned long long> h_knn(static_cast<size_t>(n) * K);
-  EPS_CUDA(cudaMemcpyAsync(h_knn.data(), knn.p, h_knn.size() * 8, cudaMemcpyDeviceToHost, ix->stream));
   EPS_CUDA(cudaStreamSynchronize(ix->stream));
   ids1.release(); dist1.release(); cnt1.release(); ids2.release(); dist2.release(); cnt2.release();
   rev.release(); rev_cnt.release(); knn.release();
 
+  // CheckConnectivity (nsg.cpp:687-775): flood from the navigation point; for the first unlinked vertex u, search
+  // the graph for u's own vector, attach u to the NEAREST ALREADY-LINKED vertex of the search pool, else to a RANDOM
+  // linked vertex; flood from u; repeat.  The searches are batched on device: the un-repaired graph is installed, the
+  // rows of all unlinked vertices go through graph_search (L2 like the rest of the refinement, beam = max(64,
+  // search_length)) and the attach / flood bookkeeping — integer work — runs on the host in the reference's order.
   std::vector<std::vector<int32_t>> extra(static_cast<size_t>(n));  // edges added by the repair
   {
     std::vector<uint8_t> seen(static_cast<size_t>(n), 0);
@@ -324,21 +347,68 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
       }
     };
     flood(static_cast<int32_t>(nav));
-    int64_t scan = 0;
-    while (linked < n) {
-      while (scan < n && seen[scan]) ++scan;  // FindUnconnectedNode: first unlinked id (:736-742)
-      if (scan >= n) break;
-      const int32_t u = static_cast<int32_t>(scan);
-      // nearest already-linked vertex among u's kNN list (the reference searches for it, :751-766)
-      int32_t root = static_cast<int32_t>(nav);
-      for (int j = 0; j < K; ++j) {
-        const unsigned long long key = h_knn[static_cast<size_t>(u) * K + j];
-        if ((key & kKeyMask) == kKeyInf) break;
-        const int32_t w = static_cast<int32_t>(key_id(key));
-        if (seen[w]) { root = w; break; }
+    if (linked < n) {
+      std::vector<int32_t> unl;
+      for (int64_t v = 0; v < n; ++v) if (!seen[v]) unl.push_back(static_cast<int32_t>(v));
+      // install the un-repaired graph for the batched searches
+      {
+        std::vector<int64_t> off0(static_cast<size_t>(n) + 1);
+        int64_t e0 = 0;
+        for (int64_t v = 0; v < n; ++v) { off0[v] = e0; e0 += h_cnt[v]; }
+        off0[n] = e0;
+        std::vector<int32_t> nb0(static_cast<size_t>(std::max<int64_t>(e0, 1)));
+        for (int64_t v = 0; v < n; ++v) std::memcpy(&nb0[off0[v]], &h_ids[static_cast<size_t>(v) * stride], static_cast<size_t>(h_cnt[v]) * 4);
+        EPS_TRY(install_csr(ix, n, off0.data(), nb0.data(), e0, nav));
       }
-      extra[root].push_back(u);  // nsg[root].push_back(id) (:774), may exceed out_degree (Q11)
-      flood(u);
+      const int64_t Ls = std::min<int64_t>(n, std::max<int>(64, bp.search_length));
+      const int64_t chunk = 32768;
+      DevBuf d_ids, d_q, d_queue;
+      EPS_TRY(d_ids.reserve(static_cast<size_t>(chunk) * 4));
+      EPS_TRY(d_q.reserve(static_cast<size_t>(chunk) * ix->dim * 4));
+      EPS_TRY(d_queue.reserve(static_cast<size_t>(chunk) * Ls * 8));
+      std::vector<unsigned long long> h_pool(static_cast<size_t>(chunk) * Ls);
+      const int saved_metric = ix->metric, saved_width = ix->search_width;
+      uint64_t rng = 0x9E3779B97F4A7C15ull ^ static_cast<uint64_t>(bp.seed);
+      int rc = EPS_OK;
+      for (size_t c0 = 0; c0 < unl.size() && rc == EPS_OK; c0 += static_cast<size_t>(chunk)) {
+        const int64_t cn = static_cast<int64_t>(std::min<size_t>(static_cast<size_t>(chunk), unl.size() - c0));
+        // many of this chunk's vertices may have been linked by earlier attachments: search only the rest
+        std::vector<int32_t> todo;
+        for (int64_t i = 0; i < cn; ++i) if (!seen[unl[c0 + i]]) todo.push_back(unl[c0 + i]);
+        if (todo.empty()) continue;
+        const int64_t tn = static_cast<int64_t>(todo.size());
+        ix->metric = EPS_METRIC_L2;
+        ix->search_width = 4;
+        rc = cudaMemcpyAsync(d_ids.p, todo.data(), static_cast<size_t>(tn) * 4, cudaMemcpyHostToDevice, ix->stream) == cudaSuccess ? EPS_OK : fail(EPS_ERR_CUDA, "repair: id upload failed");
+        if (rc == EPS_OK) rc = gather_rows(ix, d_ids.as<int32_t>(), tn, d_q.as<float>());
+        if (rc == EPS_OK) rc = graph_search(ix, d_q.as<float>(), tn, Ls, d_queue.as<unsigned long long>(), &st);
+        ix->metric = saved_metric;
+        ix->search_width = saved_width;
+        if (rc == EPS_OK && cudaMemcpyAsync(h_pool.data(), d_queue.p, static_cast<size_t>(tn) * Ls * 8, cudaMemcpyDeviceToHost, ix->stream) != cudaSuccess)
+          rc = fail(EPS_ERR_CUDA, "repair: pool download failed");
+        if (rc == EPS_OK && cudaStreamSynchronize(ix->stream) != cudaSuccess) rc = fail(EPS_ERR_CUDA, "repair: search failed");
+        if (rc != EPS_OK) break;
+        for (int64_t i = 0; i < tn; ++i) {
+          const int32_t u = todo[i];
+          if (seen[u]) continue;  // reached through an earlier attachment of this chunk
+          int32_t root = -1;
+          const unsigned long long* pool = &h_pool[static_cast<size_t>(i) * Ls];
+          for (int64_t j = 0; j < Ls; ++j) {  // nearest linked vertex of the search pool (:757-766)
+            if ((pool[j] & kKeyMask) == kKeyInf) break;
+            const int32_t w = static_cast<int32_t>(key_id(pool[j]));
+            if (w != u && seen[w]) { root = w; break; }
+          }
+          while (root < 0) {  // a random linked vertex (:767-774)
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            const int32_t r = static_cast<int32_t>((rng >> 33) % static_cast<uint64_t>(n));
+            if (seen[r]) root = r;
+          }
+          extra[root].push_back(u);  // nsg[root].push_back(id) (:774), may exceed out_degree (Q11)
+          flood(u);
+        }
+      }
+      ix->graph_counters_pending = false;
+      if (rc != EPS_OK) return rc;
     }
   }
   std::vector<int64_t> off(static_cast<size_t>(n) + 1);
@@ -351,21 +421,7 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
     for (int j = 0; j < h_cnt[v]; ++j) nb[o++] = h_ids[static_cast<size_t>(v) * stride + j];
     for (int32_t w : extra[v]) nb[o++] = w;
   }
-  // install
-  if (ix->d_offsets) { cudaFree(ix->d_offsets); ix->d_offsets = nullptr; }
-  if (ix->d_nbrs) { cudaFree(ix->d_nbrs); ix->d_nbrs = nullptr; }
-  if (ix->d_init_ids) { cudaFree(ix->d_init_ids); ix->d_init_ids = nullptr; }
-  if (ix->d_ell) { cudaFree(ix->d_ell); ix->d_ell = nullptr; }
-  ix->seed_rows_L = 0;
-  ix->init_L = 0;
-  EPS_CUDA(cudaMalloc(&ix->d_offsets, (static_cast<size_t>(n) + 1) * 8));
-  EPS_CUDA(cudaMalloc(&ix->d_nbrs, std::max<size_t>(static_cast<size_t>(e), 1) * 4));
-  EPS_CUDA(cudaMemcpyAsync(ix->d_offsets, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ix->stream));
-  if (e > 0) EPS_CUDA(cudaMemcpyAsync(ix->d_nbrs, nb.data(), nb.size() * 4, cudaMemcpyHostToDevice, ix->stream));
-  EPS_CUDA(cudaStreamSynchronize(ix->stream));
-  ix->n_indexed = n;
-  ix->n_edges = e;
-  ix->nav = nav;
+  EPS_TRY(install_csr(ix, n, off.data(), nb.data(), e, nav));
   return EPS_OK;
 }
 

@@ -44,7 +44,7 @@ constexpr int kEll = 64;        // adjacency ids per fixed-stride row
 constexpr int kGsThreads = 128;
 constexpr int kMaxW = 8;        // candidates picked per iteration (upper bound)
 constexpr int kPC = 128;        // accepted keys pending their merge (= one key per thread in the merge)
-constexpr int kFC = 1024;       // fresh-id FIFO capacity (power of two >= kMaxW * kEll + kMaxR + kGsThreads)
+constexpr int kFC = 1024;       // fresh-id FIFO capacity at W = 8 (power of two >= kMaxW * kEll + kMaxR + kGsThreads)
 constexpr int kMaxR = 32;       // ring slots (upper bound; one issuing lane per slot)
 constexpr int kRounds = kMaxW * kEll / kGsThreads;  // adjacency slots per thread
 
@@ -67,7 +67,8 @@ struct GSArgs {
   int nq;
   int W;                          // candidates per iteration (1 in exact mode)
   int exact;
-  int R;                          // ring slots
+  int R;                          // ring slots (slot s is owned by 8-lane team s & 15)
+  int fc;                         // fresh-id FIFO capacity (power of two)
   int slot_bytes;                 // ring slot pitch (row bytes, multiple of 16); 0 when rows are not staged
 };
 
@@ -169,7 +170,7 @@ __device__ __forceinline__ void merge_pending(unsigned long long* qa, unsigned l
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kGsThreads, 4) graph_search_kernel(GSArgs a) {
+__global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
   extern __shared__ __align__(128) unsigned char gs_smem[];
   const int dim4p = (a.dim + 3) & ~3;
   unsigned char* ring = gs_smem;                                                                   // [R][slot_bytes]
@@ -179,18 +180,19 @@ __global__ void __launch_bounds__(kGsThreads, 4) graph_search_kernel(GSArgs a) {
   unsigned long long* bars = cs + kPC;                                                             // [kMaxR]
   float* qv = reinterpret_cast<float*>(bars + kMaxR);                                              // [dim4p]
   int* pos = reinterpret_cast<int*>(qv + dim4p);                                                   // [kPC]
-  int* fifo = pos + kPC;                                                                           // [kFC]
-  int* slot_id = fifo + kFC;                                                                       // [kMaxR]
+  int* fifo = pos + kPC;                                                                           // [fc]
   __shared__ int s_q, s_ncur, s_cursor, s_npend, s_ncont;
+  __shared__ unsigned s_head;                      // FIFO entries [s_head, fifo_tail) are not yet issued to the ring
   __shared__ int s_cid[kMaxW];
   __shared__ int s_wcnt[kRounds][kGsThreads / 32];
   __shared__ long long s_cont_e[kMaxW], s_cont_end[kMaxW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int team = lane >> 3, tl = lane & 7;
+  const int team = lane >> 3, tl = lane & 7, team16 = warp * 4 + team;  // 16 teams of 8 lanes
   const unsigned team_mask = 0xFFu << (team * 8);
   const unsigned lane_lt = (1u << lane) - 1u;
   const int L = a.L, R = a.R, W = a.W;
+  const unsigned fmask = static_cast<unsigned>(a.fc) - 1u;
   const bool staged = a.slot_bytes > 0;
   const uint32_t ring0 = smem_u32(ring), bar0 = smem_u32(bars);
   const uint32_t row_bytes = static_cast<uint32_t>(a.dim) * 4u;
@@ -200,8 +202,11 @@ __global__ void __launch_bounds__(kGsThreads, 4) graph_search_kernel(GSArgs a) {
     for (int s = 0; s < R; ++s) mbar_init(bar0 + 8 * s, 1);
     mbar_fence_init();
   }
-  // rows that went through the ring since the kernel started: slot = g % R, mbarrier phase parity = (g / R) & 1
-  uint32_t n_issued = 0, n_consumed = 0;
+  // Ring slot s belongs to team (s & 15) for the whole kernel: the team issues the bulk copy into it, waits on its
+  // mbarrier, reads it and refills it — no block barrier guards a slot.  Per-slot state lives in the team's registers.
+  bool occ[2] = {false, false};
+  uint32_t par[2] = {0u, 0u};
+  int sid[2] = {0, 0};
   unsigned long long st_ndist = 0, st_nexp = 0, st_nedge = 0;
 
   for (;;) {
@@ -223,198 +228,212 @@ __global__ void __launch_bounds__(kGsThreads, 4) graph_search_kernel(GSArgs a) {
       }
       qa[i] = key;
     }
-    if (tid == 0) { s_npend = 0; s_ncont = 0; s_cursor = 0; s_ncur = 0; }
+    if (tid == 0) { s_npend = 0; s_ncont = 0; s_cursor = 0; s_ncur = 0; s_head = 0u; }
     __syncthreads();
     block_bitonic_sort(qa, a.Lp);
     if (tid == 0) st_ndist += static_cast<unsigned long long>(L);
-    uint32_t fifo_head = 0, fifo_tail = 0;  // fresh ids: [head, tail) not yet issued to the ring
+    uint32_t fifo_tail = 0;
 
     // ---- best-first loop (SearchImpl) ----
     for (;;) {
-      // A runs when the ring cannot be kept full from the backlog alone (wide) / when the previous expansion
-      // has been fully consumed and merged (exact)
-      const bool want = a.exact ? (fifo_tail == fifo_head && n_issued == n_consumed)
-                                : (fifo_tail - fifo_head) < static_cast<uint32_t>(R);
-      int ncur = 0, ncont = 0;
-      if (want) {
-        // -- A0: pick up to W unchecked candidates, smallest first, from queue ∪ pending (warp 0) --
-        if (warp == 0) {
-          int cnt = 0;
-          if (s_ncont == 0) {
-            const int np = s_npend;
-            int sp = s_cursor;
-            unsigned long long pk = ~0ull;  // smallest unchecked pending key (recomputed after a pending pick)
-            bool pscan = np > 0;
-            while (cnt < W) {
-              int qpos = -1;
-              for (int p = sp; p < L; p += 32) {
-                const int idx = p + lane;
-                const bool un = idx < L && !(qa[idx] & kCheckedBit);
-                const unsigned b = __ballot_sync(kFull, un);
-                if (b) { qpos = p + __ffs(b) - 1; break; }
-              }
-              const unsigned long long qkey = qpos >= 0 ? (qa[qpos] & kKeyMask) : ~0ull;
-              if (pscan) {
-                unsigned long long best = ~0ull;
-                for (int i = lane; i < np; i += 32) {
-                  const unsigned long long k = pend[i];
-                  if (!(k & kCheckedBit) && k < best) best = k;
-                }
-                unsigned long long mn = best;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  const unsigned long long other = __shfl_xor_sync(kFull, mn, o);
-                  mn = other < mn ? other : mn;
-                }
-                pk = mn;
-                pscan = false;
-              }
-              if (qpos < 0 && pk == ~0ull) break;
-              if (qkey <= pk) {
-                if (lane == 0) { qa[qpos] |= kCheckedBit; s_cid[cnt] = static_cast<int>(key_id(qkey)); }
-                sp = qpos + 1;
-              } else {
-                // keys are distinct: exactly one lane owns the pending minimum and marks it
-                for (int i = lane; i < np; i += 32) {
-                  if (pend[i] == pk) { pend[i] = pk | kCheckedBit; s_cid[cnt] = static_cast<int>(key_id(pk)); }
-                }
-                pk = ~0ull;
-                pscan = true;
-              }
-              ++cnt;
-              __syncwarp();
-            }
-            if (lane == 0) s_cursor = sp;
-          }
-          if (lane == 0) s_ncur = cnt;
-        }
-        __syncthreads();  // (1)
-        ncur = s_ncur;
-        ncont = s_ncont;
-        if (ncur == 0 && ncont == 0 && fifo_tail == fifo_head && n_issued == n_consumed) break;  // nothing left anywhere
-
-        if (ncur > 0 || ncont > 0) {
-          // -- A1: adjacency ids -> visited test-and-set -> ordered compaction of the fresh ids into the FIFO --
-          const bool cont_mode = ncur == 0;  // draining the CSR continuation of a row longer than kEll
-          long long e0 = 0;
-          int nslots = ncur * kEll;
-          if (cont_mode) {
-            e0 = s_cont_e[ncont - 1];
-            nslots = static_cast<int>(min(static_cast<long long>(kGsThreads), s_cont_end[ncont - 1] - e0));
-          }
-          int nb[kRounds];
-          unsigned bal[kRounds];
-          bool fr[kRounds];
-#pragma unroll
-          for (int r = 0; r < kRounds; ++r) {
-            const int s = r * kGsThreads + tid;
-            nb[r] = -1;
-            if (s < nslots)
-              nb[r] = cont_mode ? a.nbrs[e0 + s] : __ldg(a.ell + static_cast<int64_t>(s_cid[s >> 6]) * kEll + (s & (kEll - 1)));
-          }
-#pragma unroll
-          for (int r = 0; r < kRounds; ++r) {
-            fr[r] = false;
-            if (nb[r] >= 0) {
-              const uint32_t bit = 1u << (nb[r] & 31);
-              fr[r] = !(atomicOr(&visited[nb[r] >> 5], bit) & bit);  // ExpandOneCandidate :403-406
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < kRounds; ++r) {
-            bal[r] = __ballot_sync(kFull, fr[r]);
-            const unsigned vb = __ballot_sync(kFull, nb[r] >= 0);
-            if (lane == 0) { s_wcnt[r][warp] = __popc(bal[r]); st_nedge += static_cast<unsigned long long>(__popc(vb)); }
-          }
-          __syncthreads();  // (2)
-          int total = 0;
-#pragma unroll
-          for (int r = 0; r < kRounds; ++r) {
-            int mine = 0;
-#pragma unroll
-            for (int w = 0; w < kGsThreads / 32; ++w) {
-              if (w == warp) mine = total;
-              total += s_wcnt[r][w];
-            }
-            if (fr[r]) fifo[(fifo_tail + static_cast<uint32_t>(mine + __popc(bal[r] & lane_lt))) & (kFC - 1)] = nb[r];
-          }
-          fifo_tail += static_cast<uint32_t>(total);
-          if (cont_mode) {
-            if (tid == 0) {
-              s_cont_e[ncont - 1] = e0 + nslots;
-              if (e0 + nslots >= s_cont_end[ncont - 1]) s_ncont = ncont - 1;
-            }
-          } else {
-            // a full fixed-stride row may continue in the CSR (rare: repair hubs, reference graphs above 64)
-#pragma unroll
-            for (int r = 0; r < kRounds; ++r) {
-              const int s = r * kGsThreads + tid;
-              if (s < nslots && (s & (kEll - 1)) == kEll - 1 && nb[r] >= 0) {
-                const int c = s_cid[s >> 6];
-                const long long eb = a.offsets[c] + kEll, ee = a.offsets[c + 1];
-                if (ee > eb) {
-                  const int i = atomicAdd(&s_ncont, 1);
-                  s_cont_e[i] = eb;
-                  s_cont_end[i] = ee;
-                }
-              }
-            }
-            if (tid == 0) st_nexp += static_cast<unsigned long long>(ncur);
-          }
-          if (tid == 0) st_ndist += static_cast<unsigned long long>(total);
-        }
-      }
-
-      // -- B: issue bulk copies of fresh rows into free ring slots;  C: consume landed rows --
-      // wide: C (rows issued one iteration ago, landed during A) then B;  exact: B then C of the same rows.
-#pragma unroll 1
-      for (int phase = 0; phase < 2; ++phase) {
-        const bool do_issue = (phase == 0) == (a.exact != 0);
-        __syncthreads();  // FIFO / slot ids / pending appends of the previous phase are visible
-        if (do_issue) {
-          const uint32_t can = min(fifo_tail - fifo_head, static_cast<uint32_t>(R) - (n_issued - n_consumed));
-          if (warp == 0 && static_cast<uint32_t>(lane) < can) {
-            const uint32_t g = n_issued + lane, slot = g % static_cast<uint32_t>(R);
-            const int id = fifo[(fifo_head + lane) & (kFC - 1)];
-            slot_id[slot] = id;
-            if (staged) {
-              const uint32_t bar = bar0 + 8 * slot;
-              mbar_expect_tx(bar, row_bytes);
-              bulk_load_1d(ring0 + slot * static_cast<uint32_t>(a.slot_bytes), a.vectors + static_cast<int64_t>(id) * a.dim, row_bytes, bar);
-            }
-          }
-          n_issued += can;
-          fifo_head += can;
-        } else {
-          const unsigned long long bound = qa[L - 1] & kKeyMask;  // worst entry as of the last merge (:546)
-          for (uint32_t r = n_consumed + warp * 4 + team; r < n_issued; r += kGsThreads / 8) {
-            const uint32_t slot = r % static_cast<uint32_t>(R);
-            const int id = slot_id[slot];
-            float p;
-            if (staged) {
-              mbar_wait(bar0 + 8 * slot, (r / static_cast<uint32_t>(R)) & 1u);
-              const float4* row = reinterpret_cast<const float4*>(ring + static_cast<size_t>(slot) * a.slot_bytes);
-              p = a.metric == EPS_METRIC_L2 ? team_partial_vec4<true>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl)
-                                            : team_partial_vec4<false>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl);
-            } else {
-              const float* row = a.vectors + static_cast<int64_t>(id) * a.dim;
-              p = a.metric == EPS_METRIC_L2 ? team_partial_scalar<true>(row, qv, a.dim, tl) : team_partial_scalar<false>(row, qv, a.dim, tl);
-            }
-            p += __shfl_xor_sync(team_mask, p, 4);
-            p += __shfl_xor_sync(team_mask, p, 2);
-            p += __shfl_xor_sync(team_mask, p, 1);
-            if (tl == 0) {
-              const unsigned long long key = make_key(finish_metric(a.metric, p), static_cast<uint32_t>(id));
-              if (key < bound) pend[atomicAdd(&s_npend, 1)] = key;  // dist > bound rejected (:424); ties by id
-            }
-          }
-          n_consumed = n_issued;
-        }
-      }
-      if (a.exact) __syncthreads();  // (wide: the consume phase was already followed by a barrier)
-      // -- D: merge the pending keys (every iteration in exact mode; when the buffer could overflow otherwise) --
+      // barrier X: pending appends, FIFO writes and slot states of the previous iteration are settled;
+      // the count is the number of ring slots with a row in flight
+      const int inflight = __syncthreads_count((tl == 0 && occ[0]) || (tl == 1 && occ[1]));
       const int m = s_npend;
-      if (m > 0 && (a.exact || m > kPC - R)) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor);
+      const uint32_t head = s_head;
+      const int ncont = s_ncont;
+      // -- D: merge the pending keys (every time in exact mode; when the buffer could overflow otherwise) --
+      const bool merged = m > 0 && (a.exact || m > kPC - R);
+      if (merged) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor);
+      const bool idle = inflight == 0 && head == fifo_tail;
+      // A runs when the ring cannot be kept full from the backlog alone (wide) / when the previous expansion
+      // has been consumed and merged (exact)
+      const bool want = a.exact ? idle : (fifo_tail - head) < static_cast<uint32_t>(R);
+
+      // -- C/B, per team: consume the landed row of each owned slot, refill the slot from the FIFO at once --
+      {
+        const unsigned long long bound = qa[L - 1] & kKeyMask;  // worst entry as of the last merge (:546)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int slot = team16 + 16 * j;
+          if (slot < R) {
+            if (occ[j]) {
+              float p;
+              if (staged) {
+                mbar_wait(bar0 + 8 * slot, par[j]);
+                par[j] ^= 1u;
+                const float4* row = reinterpret_cast<const float4*>(ring + static_cast<size_t>(slot) * a.slot_bytes);
+                p = a.metric == EPS_METRIC_L2 ? team_partial_vec4<true>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl)
+                                              : team_partial_vec4<false>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl);
+              } else {
+                const float* row = a.vectors + static_cast<int64_t>(sid[j]) * a.dim;
+                p = a.metric == EPS_METRIC_L2 ? team_partial_scalar<true>(row, qv, a.dim, tl) : team_partial_scalar<false>(row, qv, a.dim, tl);
+              }
+              p += __shfl_xor_sync(team_mask, p, 4);
+              p += __shfl_xor_sync(team_mask, p, 2);
+              p += __shfl_xor_sync(team_mask, p, 1);  // every lane of the team has finished reading the slot
+              if (tl == 0) {
+                const unsigned long long key = make_key(finish_metric(a.metric, p), static_cast<uint32_t>(sid[j]));
+                if (key < bound) pend[atomicAdd(&s_npend, 1)] = key;  // dist > bound rejected (:424); ties by id
+              }
+              occ[j] = false;
+            }
+            unsigned idx = 0;
+            if (tl == 0) {
+              idx = atomicAdd(&s_head, 1u);
+              if (idx >= fifo_tail) atomicSub(&s_head, 1u);  // nothing left: hand the index back
+            }
+            idx = __shfl_sync(team_mask, idx, team * 8);
+            if (idx < fifo_tail) {
+              sid[j] = fifo[idx & fmask];
+              occ[j] = true;
+              if (staged && tl == 0) {
+                const uint32_t bar = bar0 + 8 * slot;
+                mbar_expect_tx(bar, row_bytes);
+                bulk_load_1d(ring0 + slot * static_cast<uint32_t>(a.slot_bytes), a.vectors + static_cast<int64_t>(sid[j]) * a.dim,
+                             row_bytes, bar);
+              }
+            }
+          }
+        }
+      }
+      if (!want) continue;
+
+      // -- A0: pick up to W unchecked candidates, smallest first, from queue ∪ pending (warp 0) --
+      if (warp == 0) {
+        int cnt = 0;
+        if (ncont == 0) {
+          const int np = merged ? 0 : m;  // entries appended during this iteration's team phase are picked next time
+          int sp = s_cursor;
+          unsigned long long pk[kPC / 32];
+#pragma unroll
+          for (int u = 0; u < kPC / 32; ++u) {
+            const int i = u * 32 + lane;
+            pk[u] = ~0ull;
+            if (i < np) { const unsigned long long k = pend[i]; if (!(k & kCheckedBit)) pk[u] = k; }
+          }
+          unsigned long long pmin = ~0ull;  // smallest unchecked pending key
+          bool pscan = np > 0;
+          while (cnt < W) {
+            int qpos = -1;
+            for (int p = sp; p < L; p += 32) {
+              const int idx = p + lane;
+              const bool un = idx < L && !(qa[idx] & kCheckedBit);
+              const unsigned b = __ballot_sync(kFull, un);
+              if (b) { qpos = p + __ffs(b) - 1; break; }
+            }
+            if (qpos < 0) sp = L;  // queue exhausted: later picks of this iteration do not rescan it
+            const unsigned long long qkey = qpos >= 0 ? (qa[qpos] & kKeyMask) : ~0ull;
+            if (pscan) {
+              unsigned long long mn = pk[0];
+#pragma unroll
+              for (int u = 1; u < kPC / 32; ++u) mn = pk[u] < mn ? pk[u] : mn;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(kFull, mn, o);
+                mn = other < mn ? other : mn;
+              }
+              pmin = mn;
+              pscan = false;
+            }
+            if (qpos < 0 && pmin == ~0ull) break;
+            if (qkey <= pmin) {
+              if (lane == 0) { qa[qpos] |= kCheckedBit; s_cid[cnt] = static_cast<int>(key_id(qkey)); }
+              sp = qpos + 1;
+            } else {
+              // keys are distinct: exactly one lane owns the pending minimum and marks it
+#pragma unroll
+              for (int u = 0; u < kPC / 32; ++u) {
+                if (pk[u] == pmin) {
+                  pk[u] = ~0ull;
+                  pend[u * 32 + lane] = pmin | kCheckedBit;
+                  s_cid[cnt] = static_cast<int>(key_id(pmin));
+                }
+              }
+              pscan = true;
+            }
+            ++cnt;
+            __syncwarp();
+          }
+          if (lane == 0) s_cursor = sp;
+        }
+        if (lane == 0) s_ncur = cnt;
+      }
+      __syncthreads();  // (1)
+      const int ncur = s_ncur;
+      if (ncur == 0 && ncont == 0) {
+        if (idle) break;  // nothing unchecked in queue ∪ pending, nothing in flight, nothing queued: done
+        continue;         // candidates may still come out of the rows in flight
+      }
+
+      // -- A1: adjacency ids -> visited test-and-set -> ordered compaction of the fresh ids into the FIFO --
+      const bool cont_mode = ncur == 0;  // draining the CSR continuation of a row longer than kEll
+      long long e0 = 0;
+      int nslots = ncur * kEll;
+      if (cont_mode) {
+        e0 = s_cont_e[ncont - 1];
+        nslots = static_cast<int>(min(static_cast<long long>(kGsThreads), s_cont_end[ncont - 1] - e0));
+      }
+      int nb[kRounds];
+      unsigned bal[kRounds];
+      bool fr[kRounds];
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int s = r * kGsThreads + tid;
+        nb[r] = -1;
+        if (s < nslots)
+          nb[r] = cont_mode ? a.nbrs[e0 + s] : __ldg(a.ell + static_cast<int64_t>(s_cid[s >> 6]) * kEll + (s & (kEll - 1)));
+      }
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        fr[r] = false;
+        if (nb[r] >= 0) {
+          const uint32_t bit = 1u << (nb[r] & 31);
+          fr[r] = !(atomicOr(&visited[nb[r] >> 5], bit) & bit);  // ExpandOneCandidate :403-406
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        bal[r] = __ballot_sync(kFull, fr[r]);
+        const unsigned vb = __ballot_sync(kFull, nb[r] >= 0);
+        if (lane == 0) { s_wcnt[r][warp] = __popc(bal[r]); st_nedge += static_cast<unsigned long long>(__popc(vb)); }
+      }
+      __syncthreads();  // (2)
+      int total = 0;
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        int mine = 0;
+#pragma unroll
+        for (int w = 0; w < kGsThreads / 32; ++w) {
+          if (w == warp) mine = total;
+          total += s_wcnt[r][w];
+        }
+        if (fr[r]) fifo[(fifo_tail + static_cast<uint32_t>(mine + __popc(bal[r] & lane_lt))) & fmask] = nb[r];
+      }
+      fifo_tail += static_cast<uint32_t>(total);
+      if (cont_mode) {
+        if (tid == 0) {
+          s_cont_e[ncont - 1] = e0 + nslots;
+          if (e0 + nslots >= s_cont_end[ncont - 1]) s_ncont = ncont - 1;
+        }
+      } else {
+        // a full fixed-stride row may continue in the CSR (rare: repair hubs, reference graphs above 64)
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+          const int s = r * kGsThreads + tid;
+          if (s < nslots && (s & (kEll - 1)) == kEll - 1 && nb[r] >= 0) {
+            const int c = s_cid[s >> 6];
+            const long long eb = a.offsets[c] + kEll, ee = a.offsets[c + 1];
+            if (ee > eb) {
+              const int i = atomicAdd(&s_ncont, 1);
+              s_cont_e[i] = eb;
+              s_cont_end[i] = ee;
+            }
+          }
+        }
+        if (tid == 0) st_nexp += static_cast<unsigned long long>(ncur);
+      }
+      if (tid == 0) st_ndist += static_cast<unsigned long long>(total);
     }
 
     // ---- results + visited reset (:711-714) ----
@@ -452,6 +471,15 @@ __global__ void gather_rows_kernel(const float* __restrict__ vectors, const int3
   if (i >= static_cast<int64_t>(n) * dim) return;
   const int r = static_cast<int>(i / dim), c = static_cast<int>(i % dim);
   out[i] = vectors[static_cast<int64_t>(ids[r]) * dim + c];
+}
+
+int gather_rows(Index* ix, const int32_t* d_ids, int64_t n, float* d_out) {
+  const int64_t tot = n * ix->dim;
+  if (tot <= 0) return EPS_OK;
+  gather_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(ix->d_vectors, d_ids, static_cast<int>(n),
+                                                                                      static_cast<int>(ix->dim), d_out);
+  EPS_CUDA(cudaGetLastError());
+  return EPS_OK;
 }
 
 // PrepareInitIds (vec_search_executor.cpp:487-516): dedup'd out-neighbours of the navigation point, then
@@ -494,12 +522,11 @@ int prepare_init_ids(Index* ix, int64_t L) {
 }
 
 
-// Ring geometry: ~48 KB of row slots per CTA (16 rows at d = 768), at least 2, at most kMaxR slots.
-// EPS_GRAPH_RING (developer knob, read once) overrides the slot count.
-static int ring_slots_for(int slot_bytes) {
-  static const int env_slots = [] { const char* e = getenv("EPS_GRAPH_RING"); return e ? atoi(e) : 0; }();
+// Ring geometry: ~48 KB of row slots per CTA (16 rows at d = 768) unless the index carries a tuning override
+// (eps_index_set_graph_tuning); at least 2, at most kMaxR slots.
+static int ring_slots_for(const Index* ix, int slot_bytes) {
   if (slot_bytes <= 0) return 16;
-  int r = env_slots > 0 ? env_slots : (48 * 1024) / slot_bytes;
+  int r = ix->graph_ring_slots > 0 ? ix->graph_ring_slots : (48 * 1024) / slot_bytes;
   return std::max(2, std::min(r, kMaxR));
 }
 
@@ -514,10 +541,11 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   const int width = std::max(1, std::min(ix->search_width, kMaxW));
   const bool staged = ix->vec4;  // 16-byte aligned rows of a multiple of 16 bytes: eligible for bulk async copies
   const int slot_bytes = staged ? dim * 4 : 0;
-  int R = ring_slots_for(slot_bytes);
+  int R = ring_slots_for(ix, slot_bytes);
+  const int fc = width > 4 ? kFC : kFC / 2;  // backlog below R + W * kEll new ids + one continuation chunk
   auto smem_for = [&](int r) {
     return static_cast<size_t>(r) * slot_bytes + static_cast<size_t>(Lp) * 8 + 2 * kPC * 8 + kMaxR * 8 +
-           static_cast<size_t>(dimp) * 4 + kPC * 4 + kFC * 4 + kMaxR * 4;
+           static_cast<size_t>(dimp) * 4 + kPC * 4 + static_cast<size_t>(fc) * 4;
   };
   while (R > 2 && smem_for(R) > 200 * 1024) --R;
   const size_t smem = smem_for(R);
@@ -526,6 +554,7 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel, kGsThreads, smem));
   if (per_sm < 1) per_sm = 1;
+  if (ix->graph_ctas_per_sm > 0) per_sm = std::min(per_sm, ix->graph_ctas_per_sm);
   const int slots = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(per_sm) * ix->num_sms));
   const int64_t words = ((ix->n_indexed + 31) / 32 + 3) & ~3ll;
   if (ix->visited_slots < slots || ix->s_visited.cap < static_cast<size_t>(slots) * words * 4) {
@@ -570,7 +599,7 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   a.stats = ix->s_misc.as<unsigned long long>();
   a.visited_words = words; a.seed_ld = seed_ld; a.dim = dim; a.metric = ix->metric;
   a.vec4 = ix->vec4 ? 1 : 0; a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
-  a.W = width; a.exact = width == 1 ? 1 : 0; a.R = R; a.slot_bytes = slot_bytes;
+  a.W = width; a.exact = width == 1 ? 1 : 0; a.R = R; a.slot_bytes = slot_bytes; a.fc = fc;
   graph_search_kernel<<<slots, kGsThreads, smem, ix->stream>>>(a);
   EPS_CUDA(cudaGetLastError());
   if (stats) {

@@ -59,6 +59,8 @@ struct Index {
   bool prefilter = false;
   bool force_brute = false;
   int search_width = 1;          // candidates expanded per iteration (1 = the reference's sequential order)
+  int graph_ring_slots = 0;      // row-ring slots per CTA of the graph kernel (0 = auto)
+  int graph_ctas_per_sm = 0;     // cap on resident CTAs (= in-flight queries) per SM (0 = occupancy limit)
 
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -116,6 +118,8 @@ int brute_force_knn_rows(Index* ix, int64_t q_start, int64_t nq, int64_t n_rows,
 int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsigned long long* d_queue,
                  eps_stats* stats);
 int prepare_init_ids(Index* ix, int64_t L);
+// out[i] = row d_ids[i] of the table (contiguous copy; used for seed rows and for the build's repair searches)
+int gather_rows(Index* ix, const int32_t* d_ids, int64_t n, float* d_out);
 int read_graph_counters(Index* ix, eps_stats* stats);
 
 // ---- finalize.cu ---------------------------------------------------------------------------

@@ -107,6 +107,10 @@ class Index:
         """1 = sequential expansion order of the reference (IntraQueryThreads=1); 2/4 = parallel expansion."""
         check(self.L.eps_index_set_search_width(self.h, int(width)))
 
+    def set_graph_tuning(self, ring_slots=0, ctas_per_sm=0):
+        """Launch geometry of the graph kernel (0 = auto): TMA row-ring slots per CTA, resident CTAs per SM."""
+        check(self.L.eps_index_set_graph_tuning(self.h, int(ring_slots), int(ctas_per_sm)))
+
     def set_coarse(self, mode):
         """0 = fp32 SIMT only, 1 = tcgen05 TF32 (default), 2 = tcgen05 bf16 mirror (exact re-score in all modes)."""
         check(self.L.eps_index_set_coarse(self.h, {"fp32": 0, "tf32": 1, "bf16": 2}.get(mode, mode)))
