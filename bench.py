@@ -1,33 +1,43 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native Epsilla vector-search hot path.
 
-Metric (BASELINE.json): QPS at recall@10 >= 0.99 on 10M x 768 float32, batch = 1024, top-10, synthetic
-iid-uniform[0,1) vectors, reported with the HBM roofline fraction of the dominant kernel and
-with the reference's own CPU path timed on the same box.
+Metric (BASELINE.json): QPS at recall@10 >= 0.99 on 10M x 768 float32, batch = 1024, top-10, reported with the
+roofline fraction of the dominant kernel and with the reference's own CPU path timed on the same box.
 
   python bench.py [--gpus N --steps K --warmup W] [--impl reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one batch of 1024 queries per GPU.  A step is timed with CUDA
-events on the index's launch stream, bracketed by barrier + synchronize, MAX over ranks.  `value` has the
-queries already resident in HBM; `e2e` goes through the host-buffer C-ABI call (eps_search_batch: H2D of the
-queries and D2H of ids/distances/counts inside the timed region).
+Workload.  SURVEY.md §8d defines two synthetic distributions: iid uniform[0,1) and a clustered one (1024 Gaussian
+centres, sigma = 0.1).  A graph index only has a recall >= 0.99 operating point on data with neighbourhood structure
+(on iid-uniform 768-d data the reference itself touches 75-95 % of a table for recall 0.99 and graph search at
+L = 2048 finds 30 % of the neighbours), so the HEADLINE workload is the clustered table — there the path
+north_star names (persistent-CTA graph search, HBM-bound) competes with the exact scan (tensor-bound) and the
+fastest mode with recall >= 0.99 is `value`; the iid-uniform table is measured in the same run and printed as the
+"uniform" record (exact scan; graph recall is listed when --uniform-graph is given).
 
-Operating point: the engine has the reference's own two search modes — exact scan (BruteForceSearch /
-PreFilter path) and graph search at queue length L.  bench sweeps the candidates (graph L in --L-sweep, then
-the exact scan), measures recall@10 against exact ground truth, and reports the fastest mode with
-recall >= 0.99 as `value`; every candidate is listed under "modes".
+One "step" = one pass of the hot path over one batch of 1024 queries per GPU.  A step is timed with CUDA events on
+the index's launch stream, bracketed by barrier + synchronize, MAX over ranks.  `value` has the queries already
+resident in HBM; `e2e` goes through the host-buffer C-ABI call (eps_search_batch: H2D of the queries and D2H of
+ids / distances / counts inside the timed region).
+
+Reference arm (--impl reference) and `cpu_baseline`: the reference's own VecSearchExecutor (oracle/_ref = its
+sources compiled unmodified) searching THE SAME CSR graph at the same queue length on the host cores, in the two
+modes of SURVEY.md §8d: (i) the reference defaults, NumExecutorPerField = 16 executors x IntraQueryThreads = 4, and
+(ii) throughput-optimal, one executor per core at IntraQueryThreads = 1.  The graph is built on the device
+beforehand (untimed set-up: the reference's own build needs days at 10M rows); the timed region is the reference's
+code only.  It runs in a child process under a timeout (a starved OpenMP team hangs the reference).
 
 Multi-GPU (N > 1): the 10M x 768 table (30.7 GB) fits one GPU, so ranks hold replicas and the query stream is
-partitioned (independent units, no data-path collective, scaling "weak": each rank searches its own 1024-query
-batch).  --shard-rows instead partitions the ROWS (config C5 shape): every rank searches the same batch over
-its shard and the per-shard top-k are exchanged with one NCCL all-gather + k-way merge kernel.
+partitioned (independent units, no data-path collective, scaling "weak").  --shard-rows instead partitions the
+ROWS (config C5 shape): every rank searches the same batch over its shard and the per-shard top-k are exchanged by
+the library itself (eps_search_batch_sharded: ncclAllGather + merge kernel on the index stream).
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -45,28 +55,37 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-child"])
     p.add_argument("--rows", type=int, default=10_000_000)
     p.add_argument("--dim", type=int, default=768)
     p.add_argument("--batch", type=int, default=1024)
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--metric", default="l2")
-    p.add_argument("--dist", default="uniform", choices=["uniform", "cluster"])
-    p.add_argument("--modes", default="graph,brute-bf16,brute-tf32", help="candidate modes: graph, brute-bf16, brute-tf32, brute-fp32")
-    p.add_argument("--L-sweep", default="512,2048", help="graph queue lengths to try")
-    p.add_argument("--graph-rows-max", type=int, default=int(os.environ.get("EPS_BENCH_GRAPH_ROWS_MAX", "0")),
-                   help="build/search the graph only when rows <= this (0 = graph mode off)")
-    p.add_argument("--width", type=int, default=4, help="graph expansion width (1 = reference sequential order)")
+    p.add_argument("--dist", default="cluster", choices=["uniform", "cluster"])
+    p.add_argument("--centers", type=int, default=1024)
+    p.add_argument("--modes", default="graph,brute-bf16", help="candidate modes: graph, brute-bf16, brute-tf32, brute-fp32")
+    p.add_argument("--L-sweep", default="256,512,1024,2048,4096", help="graph queue lengths, ascending; stops at the first that reaches the recall target")
+    p.add_argument("--width", type=int, default=8, help="graph search width (1 = the reference's sequential order)")
+    p.add_argument("--ring", type=int, default=0, help="graph kernel: TMA row-ring slots per CTA (0 = auto)")
+    p.add_argument("--ctas", type=int, default=0, help="graph kernel: resident CTAs per SM (0 = auto)")
+    p.add_argument("--knn-k", type=int, default=64)
+    p.add_argument("--nnd-iters", type=int, default=10)
+    p.add_argument("--uniform-record", type=int, default=1, help="also measure the iid-uniform table (exact scan)")
+    p.add_argument("--uniform-graph", action="store_true", help="also build + search a graph on the iid-uniform table")
     p.add_argument("--shard-rows", action="store_true")
     p.add_argument("--recall-target", type=float, default=0.99)
-    p.add_argument("--cpu-queries", type=int, default=32)
+    p.add_argument("--cpu-queries", type=int, default=256)
+    p.add_argument("--cpu-timeout", type=int, default=420)
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--graph-file", default="", help="(reference-child) npz with the CSR to search")
+    p.add_argument("--L", type=int, default=0, help="(reference arm) queue length; 0 = take it from the graph file / 512")
     return p.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------------
-# synthetic data (identical bits on every rank / in the reference arm: torch CPU generator is not used for
-# the 30 GB table — it is generated on device in 1M-row chunks from a seeded Philox stream)
+# synthetic data (identical bits on every rank and in the reference arm: generated on device in 1M-row chunks from
+# a seeded Philox stream; the CPU generator of the same seed is a different stream and is only used when no GPU
+# is present, i.e. in the CPU contract test)
 # ------------------------------------------------------------------------------------------------------
 def gen_table(rows, dim, dist, seed, device, centers_n=1024):
     import torch
@@ -117,7 +136,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -163,96 +182,269 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def workload_name(a, extra=""):
+    data = "iid-uniform[0,1)" if a.dist == "uniform" else "clustered (%d Gaussian centres, sigma=0.1)" % a.centers
+    return "%dx%d f32 %s %s (seed 42), batch=%d, top-%d%s" % (a.rows, a.dim, a.metric, data, a.batch, a.k, extra)
+
+
 # ------------------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle/_ref = the reference's own sources compiled unmodified)
 # ------------------------------------------------------------------------------------------------------
-class CpuReference:
-    """VecSearchExecutor::Search of the reference on the host cores (oracle/_ref = the reference's own sources
-    compiled unmodified; the scalar C port only if that library did not travel).  graph=None -> the brute-force
-    branch (no graph: the path the reference takes for an un-indexed table); else (n_indexed, offsets, nbrs, nav)
-    -> graph search on the SAME CSR the GPU used.  The table is loaded once; search() is timed per call."""
+def reference_child(a):
+    """Child process: load the table (regenerated with the same seed on the device when there is one) and the CSR
+    from --graph-file, then time VecSearchExecutor::Search on the host cores.  Prints one JSON object."""
+    import torch
+    from oracle import oracle
+    g = np.load(a.graph_file, allow_pickle=False)
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    X = gen_table(a.rows, a.dim, a.dist, 42, dev, a.centers)
+    if a.metric == "cosine":
+        X /= X.norm(dim=1, keepdim=True)
+    cores = os.cpu_count() or 1
+    kind = "reference" if oracle.have_ref() else "port"
+    n_indexed = int(g["n_indexed"])
+    L = int(a.L or g["L"])
+    out = {"kind": kind, "cores": cores, "L": L, "graph": n_indexed > 0, "modes": {}}
+    queries = g["queries"]  # [steps_total, nq, dim]
+    if kind != "reference":
+        Xh = X.cpu().numpy()
+        port = oracle.Port()
+        vals = []
+        for s in range(queries.shape[0]):
+            t0 = time.perf_counter()
+            kw = dict(metric=a.metric, vectors=Xh, queries=queries[s], limit=a.k, L=L)
+            if n_indexed > 0:
+                kw.update(n_indexed=n_indexed, offsets=g["offsets"], nbrs=g["nbrs"].astype(np.int64), nav=int(g["nav"]))
+            port.search_batch(**kw)
+            vals.append(queries.shape[1] / (time.perf_counter() - t0))
+        out["modes"]["port_T1"] = {"qps": vals, "n_exec": 1, "T": 1}
+        print(json.dumps(out))
+        return
+    r = oracle.Ref(a.metric, a.dim, a.rows, [("ID", "int4")])
+    step = 1_000_000
+    for r0 in range(0, a.rows, step):  # device -> the reference's own table, chunked (no second 30 GB host copy)
+        r.vectors[r0:min(a.rows, r0 + step)] = X[r0:r0 + step].cpu().numpy()
+    del X
+    r.set_row_count(a.rows)
+    if n_indexed > 0:
+        r.set_graph(n_indexed, g["offsets"], g["nbrs"].astype(np.int64), int(g["nav"]))
+        plans = [("i_defaults_16x4", min(16, max(1, cores // 4)), 4), ("ii_one_executor_per_core", cores, 1)]
+    else:
+        n_exec = min(16, cores)
+        plans = [("brute_force_branch", n_exec, max(1, cores // n_exec))]
+    for name, n_exec, T in plans:
+        r.make_executors(n_exec, T, L)
+        vals = []
+        for s in range(queries.shape[0]):
+            t0 = time.perf_counter()
+            r.search_batch(queries[s], a.k)
+            vals.append(queries.shape[1] / (time.perf_counter() - t0))
+        out["modes"][name] = {"qps": vals, "n_exec": n_exec, "T": T}
+    # sequential-order results (IntraQueryThreads = 1, one executor) of the first 32 queries of step 0: parity sample
+    if n_indexed > 0:
+        r.make_executors(1, 1, L)
+        ids, _, _ = r.search_batch(queries[0][:32], a.k)
+        out["ids_T1_step0"] = ids.tolist()
+    print(json.dumps(out))
 
-    def __init__(self, X_host, metric, graph=None, L=500, n_exec=None):
-        from oracle import oracle
-        self.cores = os.cpu_count() or 1
-        self.n, self.d = X_host.shape
-        self.kind = "reference" if oracle.have_ref() else "port"
-        self.metric, self.graph, self.L, self.X = metric, graph, L, X_host
-        if self.kind == "reference":
-            r = oracle.Ref(metric, self.d, self.n, [("ID", "int4")])
-            r.vectors[:self.n] = X_host
-            r.set_row_count(self.n)
-            if graph is None:
-                self.n_exec = min(n_exec or 16, self.cores)
-                self.T = max(1, self.cores // self.n_exec)  # BruteForceSearch parallelises its distance loop with OpenMP
-            else:
-                r.set_graph(*graph)
-                self.n_exec, self.T = self.cores, 1          # throughput-optimal: one executor per core (BASELINE.md 3.3b)
-            r.make_executors(self.n_exec, self.T, L)
-            self.r = r
+
+def run_reference_child(a, graph, L, queries, timeout):
+    """Spawn the child on `graph` = (n_indexed, offsets, nbrs, nav) or None; queries [steps, nq, dim] float32."""
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(tmpdir, "eps_bench_graph_%d.npz" % os.getpid())
+    try:
+        if graph is None:
+            np.savez(path, n_indexed=0, offsets=np.zeros(1, np.int64), nbrs=np.zeros(0, np.int32), nav=0, L=L, queries=queries)
         else:
-            self.port = oracle.Port()
-            self.n_exec, self.T = 1, 1
+            np.savez(path, n_indexed=graph[0], offsets=graph[1], nbrs=np.asarray(graph[2], np.int32), nav=graph[3], L=L,
+                     queries=queries)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-child", "--graph-file", path, "--rows", str(a.rows),
+               "--dim", str(a.dim), "--dist", a.dist, "--centers", str(a.centers), "--metric", a.metric, "--k", str(a.k), "--L", str(L)]
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "OMP_THREAD_LIMIT"):
+            env.pop(k, None)  # torchrun sets OMP_NUM_THREADS=1 for its workers; the reference sizes its own teams
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if p.returncode != 0 or not lines:
+            raise RuntimeError("reference child failed rc=%d: %s" % (p.returncode, p.stderr[-400:]))
+        return json.loads(lines[-1])
+    finally:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
 
-    def search(self, Q_host, k):
-        Qs = np.ascontiguousarray(Q_host)
+
+def build_graph_for_reference(a, dev):
+    """Set-up of the reference arm: a CSR over the table.  On a GPU box it is built on the device by the library (the
+    reference's own build is infeasible at 10M rows); without a GPU (CPU contract test) the reference builds it
+    itself when the table is small; otherwise there is no graph and the reference takes its brute-force branch."""
+    import torch
+    if torch.cuda.is_available():
+        import vectordb_b200
+        X = gen_table(a.rows, a.dim, a.dist, 42, dev, a.centers)
+        if a.metric == "cosine":
+            X /= X.norm(dim=1, keepdim=True)
+        ix = vectordb_b200.Index(a.metric, a.dim, capacity=a.rows, device=0)
+        ix.adopt_device_rows(X.data_ptr(), a.rows)
         t0 = time.perf_counter()
-        if self.kind == "reference":
-            ids, ds, cnt = self.r.search_batch(Qs, k)
-        else:
-            kw = dict(metric=self.metric, vectors=self.X, queries=Qs, limit=k, L=self.L)
-            if self.graph is not None:
-                kw.update(n_indexed=self.graph[0], offsets=self.graph[1], nbrs=self.graph[2], nav=self.graph[3])
-            ids, ds, cnt, _ = self.port.search_batch(**kw)
-        dt = time.perf_counter() - t0
-        return len(Qs) / dt, ids
-
-    def describe(self, nq):
-        return "%d queries of the step's batch over all %d rows, %d executors x %d threads" % (nq, self.n, self.n_exec, self.T)
+        ix.build(a.rows, knn_k=a.knn_k, nnd_iters=a.nnd_iters)
+        torch.cuda.synchronize()
+        g = ix.get_graph()
+        ix.close()
+        del X
+        torch.cuda.empty_cache()
+        return g, "built on device by libepsilla_b200 in %.0f s (set-up, untimed)" % (time.perf_counter() - t0)
+    if a.rows <= 200_000:
+        from oracle import oracle
+        if oracle.have_ref():
+            X = gen_table(a.rows, a.dim, a.dist, 42, "cpu", a.centers).numpy()
+            r = oracle.Ref(a.metric, a.dim, a.rows, [("ID", "int4")])
+            r.set_rows(X)
+            g = r.build(a.rows, threads=os.cpu_count() or 1)
+            return g, "built by the reference itself (RebuildThreads = %d)" % (os.cpu_count() or 1)
+    return None, "no graph: the reference's brute-force branch"
 
 
 def run_reference_arm(a):
-    """--impl reference: the reference's own CPU implementation of the path, timed on the host cores on a
-    bounded sample of the same workload.  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, searching the same
+    kind of CSR at the queue length the GPU arm operates at (--L, default 512).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    X = gen_table(a.rows, a.dim, a.dist, 42, dev)
-    Xh = X.cpu().numpy()
-    del X
-    nq = max(1, min(a.cpu_queries // 4, a.batch))  # bounded sample per step: the whole run ends within minutes
-    ref = CpuReference(Xh, a.metric, None, 500, n_exec=nq)  # one executor per sampled query, all host threads busy
-    vals = []
-    for s in range(a.warmup + a.steps):
-        Q = gen_queries(a.batch, a.dim, a.dist, 43 + s * 64, dev).cpu().numpy()
-        qps, _ = ref.search(Q[:nq], a.k)
-        if s >= a.warmup:
-            vals.append(qps)
-    kind, used, sample = ref.kind, ref.n_exec * ref.T, ref.describe(nq)
-    v = float(np.mean(vals))
+    graph, how = build_graph_for_reference(a, dev)
+    L = a.L or 512
+    n_steps = a.warmup + a.steps
+    Q = np.stack([gen_queries(a.batch, a.dim, a.dist, 43 + s * 64, dev, a.centers).cpu().numpy() for s in range(n_steps)])
+    if a.metric == "cosine":
+        Q /= np.linalg.norm(Q, axis=2, keepdims=True)
+    res = run_reference_child(a, graph, L, Q.astype(np.float32), timeout=max(600, a.cpu_timeout * 3))
+    best_name = max(res["modes"], key=lambda m: float(np.mean(res["modes"][m]["qps"][a.warmup:])))
+    best = res["modes"][best_name]
+    v = float(np.mean(best["qps"][a.warmup:]))
+    sample = "every step = the full batch of %d queries, %s, L=%d, %d executors x %d threads; graph %s" % (
+        a.batch, best_name, res["L"], best["n_exec"], best["T"], how)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1000.0 * a.batch / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%dx%d f32 %s %s, batch=%d, top-%d, exact scan (reference BruteForceSearch branch)" % (
-            a.rows, a.dim, a.metric, a.dist, a.batch, a.k)},
-        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": used, "kind": kind, "sample": sample},
+        "config": {"workload": workload_name(a, ", reference VecSearchExecutor on the host cores (%s)" % (
+            "graph search L=%d on the same CSR" % res["L"] if res["graph"] else "BruteForceSearch branch"))},
+        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": best["n_exec"] * best["T"], "kind": res["kind"], "sample": sample,
+                         "modes": {m: float(np.mean(x["qps"][a.warmup:])) for m, x in res["modes"].items()}},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ------------------------------------------------------------------------------------------------------
+def recall_of(truth, ids, k):
+    t, g = truth.cpu().numpy(), ids.cpu().numpy()
+    return float(np.mean([len(set(g[i].tolist()) & set(t[i].tolist())) / k for i in range(t.shape[0])]))
+
+
+def classify_misses(truth_i, truth_d, got_i, got_d, k, tol=1e-4):
+    """Misses of `got` against the exact fp32 scan: a 'tie' is an id swapped for one at the same distance (within
+    `tol` relative of the k-th exact distance), anything else is a real loss."""
+    ties = real = 0
+    for q in range(truth_i.shape[0]):
+        tset = set(truth_i[q].tolist())
+        missing = tset - set(got_i[q].tolist())
+        if not missing:
+            continue
+        kth = float(truth_d[q, k - 1])
+        extra = [j for j in range(k) if int(got_i[q, j]) not in tset]
+        for _, j in zip(missing, extra):
+            if abs(float(got_d[q, j]) - kth) <= tol * max(abs(kth), 1e-30):
+                ties += 1
+            else:
+                real += 1
+        real += max(0, len(missing) - len(extra))
+    return {"ties": ties, "real": real}
+
+
+class Arena:
+    """One table on the device with its index, query pool and exact ground truth."""
+
+    def __init__(self, a, dist_name, dev, local, rank, world, seed_shift=0):
+        import torch
+        import vectordb_b200
+        self.a, self.dev, self.dist_name = a, dev, dist_name
+        self.rows = a.rows
+        self.X = gen_table(a.rows, a.dim, dist_name, 42 + seed_shift, dev, a.centers)
+        n_pool = a.warmup + a.steps
+        qseed = lambda s: 43 + s * 64 + (0 if a.shard_rows else rank)
+        self.Qpool = [gen_queries(a.batch, a.dim, dist_name, qseed(s), dev, a.centers) for s in range(n_pool)]
+        if a.metric == "cosine":
+            self.X /= self.X.norm(dim=1, keepdim=True)
+            self.Qpool = [q / q.norm(dim=1, keepdim=True) for q in self.Qpool]
+        self.ix = vectordb_b200.Index(a.metric, a.dim, capacity=a.rows, device=local)
+        self.ix.adopt_device_rows(self.X.data_ptr(), a.rows)
+        self.out_ids = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
+        self.out_d = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
+        self.out_c = torch.empty((a.batch,), dtype=torch.int64, device=dev)
+        self.stream = torch.cuda.ExternalStream(self.ix.stream, device=dev)
+
+    def search(self, q, **kw):
+        return self.ix.search_device(q.data_ptr(), self.a.batch, self.a.k, self.out_ids.data_ptr(), self.out_d.data_ptr(),
+                                     self.out_c.data_ptr(), **kw)
+
+    def ground_truth(self):
+        """fp32 SIMT exact scan (no tensor-core coarse pass) of Qpool[0], cross-checked in fp64 on 4 queries."""
+        import torch
+        a, dev = self.a, self.dev
+        self.ix.config(512, 512, force_brute=True)
+        self.ix.set_coarse("fp32")
+        self.search(self.Qpool[0])
+        self.truth, self.truth_d = self.out_ids.clone(), self.out_d.clone()
+        with torch.no_grad():
+            qs = self.Qpool[0][:4].double()
+            best = torch.full((4, a.k), float("inf"), device=dev, dtype=torch.float64)
+            bid = torch.zeros((4, a.k), dtype=torch.int64, device=dev)
+            for r0 in range(0, self.rows, 500_000):
+                xb = self.X[r0:r0 + 500_000].double()
+                if a.metric == "l2":
+                    dd = (qs * qs).sum(1)[:, None] - 2 * qs @ xb.T + (xb * xb).sum(1)[None, :]
+                elif a.metric == "ip":
+                    dd = -(qs @ xb.T)
+                else:
+                    dd = 1 - qs @ xb.T
+                cat_d = torch.cat([best, dd], 1)
+                cat_i = torch.cat([bid, torch.arange(r0, r0 + xb.shape[0], device=dev)[None, :].expand(4, -1)], 1)
+                best, sel = torch.topk(cat_d, a.k, dim=1, largest=False)
+                bid = torch.gather(cat_i, 1, sel)
+                del xb, dd
+            chk = float(np.mean([len(set(bid[i].tolist()) & set(self.truth[i].tolist())) / a.k for i in range(4)]))
+        assert chk >= 0.99, "exact-scan ground truth disagrees with the fp64 check: %.3f" % chk
+        return chk
+
+    def set_mode(self, m):
+        a = self.a
+        if m[0] == "graph":
+            self.ix.config(m[1], m[1], force_brute=False)
+            self.ix.set_search_width(a.width)
+            self.ix.set_graph_tuning(a.ring, a.ctas)
+        else:
+            self.ix.config(512, 512, force_brute=True)
+            self.ix.set_coarse(m[2])
+
+    def close(self):
+        self.ix.close()
+        del self.X, self.Qpool
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
         return
+    if a.impl == "reference-child":
+        reference_child(a)
+        return
     import torch
     import torch.distributed as dist
-    import vectordb_b200
-    from vectordb_b200.index import merge_shards_device
+    import vectordb_b200  # noqa: F401  (fails loudly when libepsilla_b200.so is missing)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -268,114 +460,79 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     hbm_peak, tf_peak, peak_src = measured_peaks()
-    rows = a.rows
-    # replicas: same table on every rank; --shard-rows: rank r holds rows [r*rows, (r+1)*rows) of an N*rows table
-    X = gen_table(rows, a.dim, a.dist, 42 + (rank if a.shard_rows else 0), dev)
-    ix = vectordb_b200.Index(a.metric, a.dim, capacity=rows, device=local)
-    ix.adopt_device_rows(X.data_ptr(), rows)
     n_pool = a.warmup + a.steps
-    # every rank searches its own batch (replicas) or the same batch (row shards)
-    qseed = lambda s: 43 + s * 64 + (0 if a.shard_rows else rank)
-    Qpool = [gen_queries(a.batch, a.dim, a.dist, qseed(s), dev) for s in range(n_pool)]
-    if a.metric == "cosine":
-        X /= X.norm(dim=1, keepdim=True)
-        Qpool = [q / q.norm(dim=1, keepdim=True) for q in Qpool]
-    out_ids = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
-    out_d = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
-    out_c = torch.empty((a.batch,), dtype=torch.int64, device=dev)
-    stream = torch.cuda.ExternalStream(ix.stream, device=dev)
+    A = Arena(a, a.dist, dev, local, rank, world, seed_shift=(rank if a.shard_rows else 0))
+    ix, rows = A.ix, a.rows
+    chk = A.ground_truth()
 
-    # ---- exact ground truth for recall (the exact-scan mode itself; cross-checked in fp64 on a sample) ----
-    ix.config(512, 512, force_brute=True)
-    ix.set_coarse("fp32")  # ground truth = the fp32 SIMT exact scan (no tensor-core coarse pass), fp64-checked below
-    Qt = Qpool[0]
-    ix.search_device(Qt.data_ptr(), a.batch, a.k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr())
-    truth = out_ids.clone()
-    truth_d = out_d.clone()
-    chk = 0.0
-    with torch.no_grad():
-        qs = Qt[:4].double()
-        best = torch.full((4, a.k), float("inf"), device=dev, dtype=torch.float64)
-        bid = torch.zeros((4, a.k), dtype=torch.int64, device=dev)
-        for r0 in range(0, rows, 500_000):
-            xb = X[r0:r0 + 500_000].double()
-            if a.metric == "l2":
-                dd = (qs * qs).sum(1)[:, None] - 2 * qs @ xb.T + (xb * xb).sum(1)[None, :]
-            elif a.metric == "ip":
-                dd = -(qs @ xb.T)
-            else:
-                dd = 1 - qs @ xb.T
-            cat_d = torch.cat([best, dd], 1)
-            cat_i = torch.cat([bid, torch.arange(r0, r0 + xb.shape[0], device=dev)[None, :].expand(4, -1)], 1)
-            best, sel = torch.topk(cat_d, a.k, dim=1, largest=False)
-            bid = torch.gather(cat_i, 1, sel)
-            del xb, dd
-        chk = float(np.mean([len(set(bid[i].tolist()) & set(truth[i].tolist())) / a.k for i in range(4)]))
-    assert chk >= 0.99, "exact-scan ground truth disagrees with the fp64 check: %.3f" % chk
+    # row shards: the exchange lives in the library (ncclAllGather + merge kernel on the index stream)
+    group = None
+    if a.shard_rows and world > 1:
+        from vectordb_b200.sharded import ShardGroup
+        uid = [ShardGroup.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        group = ShardGroup(uid[0], rank, world, local)
+        m_ids = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
+        m_d = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
 
-    def recall_of(ids):
-        t, g = truth.cpu().numpy(), ids.cpu().numpy()
-        return float(np.mean([len(set(g[i].tolist()) & set(t[i].tolist())) / a.k for i in range(a.batch)]))
-
-    # ---- candidate modes ----
-    modes = []
-    want = [m.strip() for m in a.modes.split(",") if m.strip()]
-    graph_ok = "graph" in want and a.graph_rows_max and rows <= a.graph_rows_max
-    build_s = None
-    if graph_ok:
-        t0 = time.perf_counter()
-        ix.build(rows, knn_k=64, nnd_iters=10)
-        torch.cuda.synchronize()
-        build_s = time.perf_counter() - t0
-        for L in [int(x) for x in a.L_sweep.split(",")]:
-            modes.append(("graph", L, ""))
-    for w in want:
-        if w.startswith("brute"):
-            modes.append(("brute", 0, w.split("-")[1] if "-" in w else "tf32"))
-    if not modes:
-        modes.append(("brute", 0, "tf32"))
-
-    def set_mode(m):
-        if m[0] == "graph":
-            ix.config(m[1], m[1], force_brute=False)
-            ix.set_search_width(a.width)
-        else:
-            ix.config(512, 512, force_brute=True)
-            ix.set_coarse(m[2])
-
-    def timed_device_steps(m, n_steps, first):
+    def timed_device_steps(m, n_steps, first, want_stats=True):
         """Device-resident inputs: CUDA events on the launch stream; max over ranks."""
-        set_mode(m)
+        A.set_mode(m)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
         stats = []
         barrier()
         for s in range(n_steps):
-            q = Qpool[(first + s) % n_pool]
-            evs[s][0].record(stream)
-            st = ix.search_device(q.data_ptr(), a.batch, a.k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr(),
-                                  want_stats=True, sync=True)
-            evs[s][1].record(stream)
-            stats.append(st)
+            q = A.Qpool[(first + s) % n_pool]
+            evs[s][0].record(A.stream)
+            if group is not None:
+                group.search(A.ix, rank * rows, q.data_ptr(), a.batch, a.k, m_ids.data_ptr(), m_d.data_ptr(), sync=True)
+                stats.append(None)
+            else:
+                stats.append(A.search(q, want_stats=want_stats, sync=True))
+            evs[s][1].record(A.stream)
         barrier()
-        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), stats
+        return max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs)), stats
 
-    report = []
-    for m in modes:
-        set_mode(m)
-        ix.search_device(Qt.data_ptr(), a.batch, a.k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr())
-        rec = recall_of(out_ids)
+    # ---- candidate modes: graph at the smallest L reaching the recall target, exact scan ----
+    want = [m.strip() for m in a.modes.split(",") if m.strip()]
+    report, build_s = [], None
+    key_rec = "recall_at_%d" % a.k
+
+    def probe(m):
+        A.set_mode(m)
+        A.search(A.Qpool[0])
+        rec = recall_of(A.truth, A.out_ids, a.k)
         timed_device_steps(m, a.warmup, 0)
         ms, stats = timed_device_steps(m, max(2, min(a.steps, 3)), a.warmup)
-        qps = world * a.batch * len(stats) / (ms / 1000.0) if not a.shard_rows else a.batch * len(stats) / (ms / 1000.0)
-        report.append({"mode": m[0], "L": m[1], "coarse": m[2], "recall_at_%d" % a.k: rec, "qps_probe": qps,
-                       "n_dist_per_query": float(np.mean([s["n_dist"] for s in stats])) / a.batch})
-    ok = [r for r in report if r["recall_at_%d" % a.k] >= a.recall_target]
-    chosen = max(ok, key=lambda r: r["qps_probe"]) if ok else max(report, key=lambda r: r["recall_at_%d" % a.k])
+        qps = (1 if a.shard_rows else world) * a.batch * len(stats) / (ms / 1000.0)
+        r = {"mode": m[0], "L": m[1], "coarse": m[2], key_rec: rec, "qps_probe": qps}
+        if stats[0] is not None:
+            r["n_dist_per_query"] = float(np.mean([s["n_dist"] for s in stats])) / a.batch
+        report.append(r)
+        return r
+
+    if "graph" in want:
+        t0 = time.perf_counter()
+        ix.build(rows, knn_k=a.knn_k, nnd_iters=a.nnd_iters)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+        for L in [int(x) for x in a.L_sweep.split(",")]:
+            if L > rows:
+                break
+            if probe(("graph", L, ""))[key_rec] >= a.recall_target:
+                break
+    for w in want:
+        if w.startswith("brute"):
+            probe(("brute", 0, w.split("-")[1] if "-" in w else "tf32"))
+    ok = [r for r in report if r[key_rec] >= a.recall_target]
+    chosen = max(ok, key=lambda r: r["qps_probe"]) if ok else max(report, key=lambda r: r[key_rec])
     mode = (chosen["mode"], chosen["L"], chosen["coarse"])
 
     # ---- timed region: `value` (inputs resident in HBM) ----
@@ -383,149 +540,197 @@ def main():
     timed_device_steps(mode, a.warmup, 0)
     clocks.start()
     ms_dev, stats = timed_device_steps(mode, a.steps, a.warmup)
-    launches = int(sum(s["kernel_launches"] for s in stats))
-    kernel_ms = float(sum(s["kernel_ms"] for s in stats))
-    n_dist = float(sum(s["n_dist"] for s in stats))
-    n_seed = float(sum(s["n_seed"] for s in stats))
-    n_exp = float(sum(s["n_expand"] for s in stats))
-    n_edges = float(sum(s["n_edges"] for s in stats))
+    have_stats = stats[0] is not None
+    launches = int(sum(s["kernel_launches"] for s in stats)) if have_stats else None
+    kernel_ms = float(sum(s["kernel_ms"] for s in stats)) if have_stats else ms_dev
+    agg = {k: float(sum(s[k] for s in stats)) if have_stats else 0.0 for k in ("n_dist", "n_seed", "n_expand", "n_edges")}
 
     # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region ----
-    set_mode(mode)
-    Qhost = [torch.empty((a.batch, a.dim), dtype=torch.float32).pin_memory().copy_(q.cpu()) for q in Qpool]
+    import ctypes as C
+    from vectordb_b200.lib import check
+    A.set_mode(mode)
+    Qhost = [torch.empty((a.batch, a.dim), dtype=torch.float32).pin_memory().copy_(q.cpu()) for q in A.Qpool]
     e_ids = np.empty((a.batch, a.k), np.int64)
     e_d = np.empty((a.batch, a.k), np.float64)
     e_c = np.empty(a.batch, np.int64)
-    import ctypes as C
-    from vectordb_b200.lib import check
+    h_ids = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
+    h_d = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
+    d_q = torch.empty((a.batch, a.dim), dtype=torch.float32, device=dev)
 
     def e2e_step(s):
         q = Qhost[s % n_pool]
-        check(ix.L.eps_search_batch(ix.h, C.c_void_p(q.data_ptr()), a.batch, a.k, None, 0, e_ids.ctypes.data_as(C.c_void_p),
-                                    e_d.ctypes.data_as(C.c_void_p), e_c.ctypes.data_as(C.c_void_p), None))
+        if group is None:
+            check(ix.L.eps_search_batch(ix.h, C.c_void_p(q.data_ptr()), a.batch, a.k, None, 0, e_ids.ctypes.data_as(C.c_void_p),
+                                        e_d.ctypes.data_as(C.c_void_p), e_c.ctypes.data_as(C.c_void_p), None))
+        else:  # row shards: H2D of the replicated batch, sharded search + exchange, D2H of the merged result
+            with torch.cuda.stream(A.stream):
+                d_q.copy_(q, non_blocking=True)
+                group.search(ix, rank * rows, d_q.data_ptr(), a.batch, a.k, m_ids.data_ptr(), m_d.data_ptr(), sync=False)
+                h_ids.copy_(m_ids, non_blocking=True)
+                h_d.copy_(m_d, non_blocking=True)
+            A.stream.synchronize()
 
     for s in range(a.warmup):
         e2e_step(s)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0.record(A.stream)
     for s in range(a.steps):
         e2e_step(a.warmup + s)
-    e1.record(stream)
+    e1.record(A.stream)
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop()
 
-    # optional row-shard exchange (all-gather of per-shard top-k + merge kernel), timed separately
-    exchange_ms = None
-    if a.shard_rows and world > 1:
-        from vectordb_b200 import sharded
-        mi = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
-        md = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
-
-        def merge_fn(all_i, all_d, kk):
-            torch.cuda.synchronize()
-            merge_shards_device(local, all_i.data_ptr(), all_d.data_ptr(), world, a.batch, kk, mi.data_ptr(), md.data_ptr())
-            return mi, md
-
-        barrier()
-        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        x0.record()
-        for _ in range(a.steps):
-            sharded.exchange_and_merge(out_ids, out_d, rank * rows, a.k, dist, merge_fn)
-        x1.record()
-        barrier()
-        exchange_ms = x0.elapsed_time(x1) / a.steps
-        # correctness of the exchange: merged results of the last timed step's batch vs merged exact ground truth
-        set_mode(mode)
-        ix.search_device(Qt.data_ptr(), a.batch, a.k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr())
-        gi, gd = sharded.exchange_and_merge(out_ids, out_d, rank * rows, a.k, dist, merge_fn)
-        got = gi.cpu().numpy().copy()
-        ti, td = sharded.exchange_and_merge(truth, truth_d, rank * rows, a.k, dist, merge_fn)
-        want = ti.cpu().numpy()
-        merged_recall = float(np.mean([len(set(got[i].tolist()) & set(want[i].tolist())) / a.k for i in range(a.batch)]))
-
     units = a.batch * a.steps * (1 if a.shard_rows else world)
-    value = units / ((ms_dev + (exchange_ms or 0.0) * a.steps) / 1000.0)
-    e2e_value = units / ((ms_e2e + (exchange_ms or 0.0) * a.steps) / 1000.0)
+    value = units / (ms_dev / 1000.0)
+    e2e_value = units / (ms_e2e / 1000.0)
 
     # ---- roofline of the dominant kernel (algorithmic bytes per SURVEY.md §8d / DESIGN.md) ----
-    if mode[0] == "brute":
-        bytes_alg = a.steps * (rows * a.dim * 4.0 + a.batch * a.dim * 4.0 + a.batch * a.k * 12.0)
-        kernel_name = "bf_dist_tile_kernel + bf_select_kernel"
-    else:
-        deg_bytes = 4.0  # int32 neighbour ids on device
-        bytes_alg = (n_dist - n_seed) * a.dim * 4.0 + n_edges * deg_bytes + n_exp * 16.0 + \
-            a.steps * (mode[1] * a.dim * 4.0) + a.steps * a.batch * (a.dim * 4.0 + a.k * 12.0)
-        kernel_name = "graph_search_kernel"
-    if mode[0] == "brute" and mode[2] != "fp32" and not os.environ.get("EPS_NO_TC"):
-        # exact scan at B=1024 is a dense contraction (512 flop/B): tcgen05 kind::tf32 coarse pass + fp32 re-score.
-        # Roofline = tensor pipe.  TF32 runs at half the bf16 rate on tcgen05, so peak = measured bf16 / 2.
-        flop = a.steps * rows * float(a.batch) * a.dim * 2.0
-        ach = flop / (kernel_ms / 1000.0) / 1e12 if kernel_ms > 0 else 0.0
-        peak = tf_peak / 2.0 if mode[2] == "tf32" else tf_peak
-        # DRAM bytes of ONE launch of the dominant kernel from the committed ncu capture of this workload
-        # (profiles/r01_ncu_tc_dist_fused_bf16_10Mx768.md: 4.04 GB read + 6.5 MB written for a 2.63 M-row launch,
-        # i.e. exactly the bf16 rows once); only quoted for the configuration it was captured on.
-        traffic = 4.039187e9 + 6.485504e6 if (mode[2] == "bf16" and rows == 10_000_000 and a.dim == 768 and a.batch == 1024) else None
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+    def graph_roofline(agg_, L_, k_ms, n_steps):
+        bytes_alg = (agg_["n_dist"] - agg_["n_seed"]) * a.dim * 4.0 + agg_["n_edges"] * 4.0 + agg_["n_expand"] * 16.0 + \
+            n_steps * (L_ * a.dim * 4.0) + n_steps * a.batch * (a.dim * 4.0 + a.k * 12.0)
+        ach = bytes_alg / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "kernel": "graph_search_kernel (persistent CTAs, cp.async.bulk row ring)", "peak_source": peak_src,
+                "kernel_ms_per_step": k_ms / n_steps, "algorithmic_bytes_per_step": bytes_alg / n_steps,
+                "n_dist_per_query": agg_["n_dist"] / (n_steps * a.batch)}
+
+    def scan_roofline(coarse, k_ms, n_steps):
+        bytes_alg = n_steps * (rows * a.dim * 4.0 + a.batch * a.dim * 4.0 + a.batch * a.k * 12.0)
+        if coarse == "fp32":
+            ach = bytes_alg / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
+            return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                    "kernel": "bf_dist_tile_kernel + bf_select_kernel", "peak_source": peak_src, "kernel_ms_per_step": k_ms / n_steps}
+        flop = n_steps * rows * float(a.batch) * a.dim * 2.0
+        ach = flop / (k_ms / 1000.0) / 1e12 if k_ms > 0 else 0.0
+        peak = tf_peak / 2.0 if coarse == "tf32" else tf_peak  # tcgen05 kind::tf32 runs at half the bf16 rate
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "kernel": "tc_dist_kernel (tcgen05 kind::%s, fused threshold select) + bf_select_kernel + rescore_kernel" % (
-                    "tf32" if mode[2] == "tf32" else "f16/bf16"),
-                "peak_source": "%s bf16 sustained (%.0f TF/s)%s" % (peak_src, tf_peak, " / 2 for TF32" if mode[2] == "tf32" else ""),
-                "kernel_ms_per_step": kernel_ms / a.steps,
-                "hbm_algorithmic_GBps": bytes_alg / (kernel_ms / 1000.0) / 1e9 if kernel_ms > 0 else 0.0}
-    else:
-        achieved = bytes_alg / (kernel_ms / 1000.0) / 1e9 if kernel_ms > 0 else 0.0
-        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": kernel_name, "peak_source": peak_src, "kernel_ms_per_step": kernel_ms / a.steps}
-        if mode[0] == "brute":
-            flop = a.steps * rows * float(a.batch) * a.dim * (3.0 if a.metric == "l2" else 2.0)
-            roof["fp32_simt_tflops"] = flop / (kernel_ms / 1000.0) / 1e12 if kernel_ms > 0 else 0.0
+                    "tf32" if coarse == "tf32" else "f16/bf16"),
+                "peak_source": "%s bf16 sustained (%.0f TF/s)%s" % (peak_src, tf_peak, " / 2 for TF32" if coarse == "tf32" else ""),
+                "kernel_ms_per_step": k_ms / n_steps,
+                "hbm_algorithmic_GBps": bytes_alg / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0}
+
+    roof = graph_roofline(agg, mode[1], kernel_ms, a.steps) if mode[0] == "graph" else scan_roofline(mode[2], kernel_ms, a.steps)
+
+    # ---- secondary records of the non-chosen modes, each with its own roofline ----
+    extra = {}
+    for r in report:
+        m = (r["mode"], r["L"], r["coarse"])
+        if m == mode or r[key_rec] < a.recall_target or group is not None:
+            continue
+        tag = "graph" if m[0] == "graph" else "exact_scan_" + m[2]
+        if tag in extra:
+            continue
+        ms, st = timed_device_steps(m, min(a.steps, 5), a.warmup)
+        k_ms = float(sum(s["kernel_ms"] for s in st))
+        ag = {k: float(sum(s[k] for s in st)) for k in ("n_dist", "n_seed", "n_expand", "n_edges")}
+        extra[tag] = {"value": world * a.batch * len(st) / (ms / 1000.0), "unit": "queries/s", key_rec: r[key_rec], "L": m[1],
+                      "roofline": graph_roofline(ag, m[1], k_ms, len(st)) if m[0] == "graph" else scan_roofline(m[2], k_ms, len(st))}
+
+    # ---- exactness accounting of the exact-scan mode against the fp32 scan (ties vs real losses) ----
+    misses = None
+    bf = [r for r in report if r["mode"] == "brute" and r["coarse"] != "fp32"]
+    if bf and group is None:
+        A.set_mode(("brute", 0, bf[0]["coarse"]))
+        A.search(A.Qpool[0])
+        misses = classify_misses(A.truth.cpu().numpy(), A.truth_d.cpu().numpy(), A.out_ids.cpu().numpy(), A.out_d.cpu().numpy(), a.k)
+        misses["queries"] = a.batch
+        misses["mode"] = "exact scan, %s coarse pass" % bf[0]["coarse"]
 
     out = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%dx%d f32 %s iid-%s (seed 42), batch=%d, top-%d, mode=%s%s; %s" % (
-            rows, a.dim, a.metric, a.dist, a.batch, a.k, mode[0], (" L=%d" % mode[1]) if mode[0] == "graph" else " (exact scan: tcgen05 %s coarse pass + fp32 re-score)" % mode[2],
-            "row shards + NCCL all-gather" if a.shard_rows else "replicated table, query stream partitioned over ranks"),
-            "recall_at_%d" % a.k: chosen["recall_at_%d" % a.k], "l2_flush": "inputs (%.1f GB table) larger than L2" % (
-                rows * a.dim * 4 / 1e9), "fp64_groundtruth_check": chk},
+        "config": {"workload": workload_name(a, ", mode=%s; %s" % (
+            ("graph search L=%d width=%d" % (mode[1], a.width)) if mode[0] == "graph" else
+            "exact scan (tcgen05 %s coarse pass + fp32 re-score)" % mode[2],
+            "row shards + in-library ncclAllGather + merge" if a.shard_rows else "replicated table, query stream partitioned over ranks")),
+            key_rec: chosen[key_rec], "l2_flush": "inputs (%.1f GB table) larger than L2" % (rows * a.dim * 4 / 1e9),
+            "fp64_groundtruth_check": chk},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.dim * 4,
-                "d2h_bytes_per_step": a.batch * a.k * 12 + a.batch * 8},
+                "d2h_bytes_per_step": a.batch * a.k * 12 + (0 if group is not None else a.batch * 8)},
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "modes": report,
     }
+    out.update(extra)
+    if misses is not None:
+        out["exact_scan_misses_vs_fp32"] = misses
     if build_s is not None:
         out["graph_build_s"] = build_s
-    if exchange_ms is not None:
-        out["exchange_ms_per_step"] = exchange_ms
-        out["merged_recall_at_%d" % a.k] = merged_recall
 
-    # ---- the reference's CPU path on this box's host cores (rank 0, N = 1 only) ----
-    if rank == 0 and world == 1 and not a.no_cpu:
+    # ---- the reference's CPU path on this box's host cores, searching the SAME CSR (rank 0) ----
+    good_graph = [r for r in report if r["mode"] == "graph" and r[key_rec] >= a.recall_target]
+    if rank == 0 and not a.no_cpu:
         try:
-            Xh = X.cpu().numpy()
-            Qh = Qpool[0].cpu().numpy()
-            graph = None
-            L = 500
-            if mode[0] == "graph":
+            graph, L = None, 500
+            if good_graph:
                 graph = ix.get_graph()
-                L = mode[1]
+                L = mode[1] if mode[0] == "graph" else good_graph[0]["L"]
             nqc = min(a.cpu_queries, a.batch)
-            ref = CpuReference(Xh, a.metric, graph, L)
-            qps, cids = ref.search(Qh[:nqc], a.k)
-            cores, kind, sample = ref.n_exec * ref.T, ref.kind, ref.describe(nqc)
-            agree = float(np.mean([len(set(cids[i].tolist()) & set(truth[i].tolist())) / a.k for i in range(len(cids))]))
-            out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample,
-                                   "ids_agree_with_gpu": agree}
+            Qc = np.stack([A.Qpool[0][:nqc].cpu().numpy(), A.Qpool[1 % n_pool][:nqc].cpu().numpy()]).astype(np.float32)
+            res = run_reference_child(a, graph, L, Qc, timeout=a.cpu_timeout)
+            modes_qps = {m: float(x["qps"][-1]) for m, x in res["modes"].items()}
+            best_name = max(modes_qps, key=modes_qps.get)
+            best = res["modes"][best_name]
+            cb = {"value": modes_qps[best_name], "unit": "queries/s", "cores": best["n_exec"] * best["T"], "kind": res["kind"],
+                  "sample": "%d queries of a step's batch, %s on the same CSR at L=%d (%d executors x %d threads, %d host cores)" % (
+                      nqc, best_name, res["L"], best["n_exec"], best["T"], res["cores"]),
+                  "modes": modes_qps}
+            if "ids_T1_step0" in res and graph is not None:
+                # parity sample: width 1 on the device vs the reference at IntraQueryThreads = 1, same CSR, same L
+                ref_ids = np.asarray(res["ids_T1_step0"], np.int64)
+                A.set_mode(("graph", L, ""))
+                ix.set_search_width(1)
+                A.search(A.Qpool[0])
+                g1 = A.out_ids.cpu().numpy()[:ref_ids.shape[0]]
+                cb["parity_sample"] = {"queries": int(ref_ids.shape[0]),
+                                       "ids_identical_width1_vs_reference_T1": float(np.mean(g1 == ref_ids)),
+                                       "queries_identical": float(np.mean(np.all(g1 == ref_ids, axis=1)))}
+                ix.set_search_width(a.width)
+            out["cpu_baseline"] = cb
         except Exception as e:  # the bench line must still print
             out["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference",
                                    "sample": "failed: %r" % (e,)}
+
+    # ---- the iid-uniform table of SURVEY.md §8d in the same run ----
+    if a.uniform_record and a.dist != "uniform" and group is None:
+        try:
+            A.close()
+            torch.cuda.empty_cache()
+            au = argparse.Namespace(**vars(a))
+            au.dist = "uniform"
+            A = Arena(au, "uniform", dev, local, rank, world)
+            A.ground_truth()
+            m = ("brute", 0, "bf16")
+            A.set_mode(m)
+            A.search(A.Qpool[0])
+            urec = recall_of(A.truth, A.out_ids, a.k)
+            umiss = classify_misses(A.truth.cpu().numpy(), A.truth_d.cpu().numpy(), A.out_ids.cpu().numpy(), A.out_d.cpu().numpy(), a.k)
+            timed_device_steps(m, a.warmup, 0)
+            ms, st = timed_device_steps(m, min(a.steps, 5), a.warmup)
+            k_ms = float(sum(s["kernel_ms"] for s in st))
+            urep = {"workload": workload_name(au, ", exact scan (tcgen05 bf16 coarse pass + fp32 re-score)"),
+                    "value": world * a.batch * len(st) / (ms / 1000.0), "unit": "queries/s", key_rec: urec,
+                    "roofline": scan_roofline("bf16", k_ms, len(st)), "misses_vs_fp32": umiss}
+            if a.uniform_graph:
+                t0 = time.perf_counter()
+                A.ix.build(rows, knn_k=a.knn_k, nnd_iters=a.nnd_iters)
+                torch.cuda.synchronize()
+                urep["graph_build_s"] = time.perf_counter() - t0
+                gm = ("graph", 2048, "")
+                A.set_mode(gm)
+                A.search(A.Qpool[0])
+                grec = recall_of(A.truth, A.out_ids, a.k)
+                ms, st = timed_device_steps(gm, 3, a.warmup)
+                urep["graph_L2048"] = {key_rec: grec, "value": world * a.batch * len(st) / (ms / 1000.0)}
+            out["uniform"] = urep
+        except Exception as e:
+            out["uniform"] = {"failed": repr(e)}
     if rank == 0:
         print(json.dumps(out))
+    if group is not None:
+        group.close()
     if world > 1:
         dist.destroy_process_group()
 

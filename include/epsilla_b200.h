@@ -180,6 +180,28 @@ EPS_API int eps_search_batch_device(eps_index* ix, const float* d_queries, int64
 EPS_API int eps_merge_shards_device(int device, const int64_t* d_ids, const float* d_dists, int64_t n_shards, int64_t nq,
                             int64_t k, int64_t* d_out_ids, float* d_out_dists);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row-sharded tables (one shard per GPU, one process or thread per GPU).  No reference counterpart: the reference
+ * is single-segment (db/table_mvp.hpp:110); its own two-source merge of graph and tail results
+ * (vec_search_executor.cpp:885-900) is the model.  The exchange (ONE ncclAllGather of nq*k*12 bytes per rank +
+ * a k-way merge kernel) runs on the index's stream inside the library; NCCL is bound at run time (libnccl.so.2).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct eps_shard_group eps_shard_group;
+
+/* 128 bytes identifying a new group: call once (on any rank), hand the bytes to every rank by any host
+ * transport (the reference engine would carry them in its cluster metadata), then create the group everywhere. */
+EPS_API int eps_shard_unique_id(void* out128);
+/* Collective over all ranks of the group (ncclCommInitRank).  device = the CUDA ordinal this rank's shard lives on. */
+EPS_API int eps_shard_group_create(eps_shard_group** out, const void* unique_id128, int rank, int world, int device);
+EPS_API void eps_shard_group_destroy(eps_shard_group* g);
+/* VecSearchExecutor::Search over a row-sharded table.  Every rank passes the SAME device-resident query batch and
+ * its own shard index; id_base = global id of the shard's row 0.  Output (device, on every rank): the merged global
+ * top-k, ids int64 [nq x k] (-1 padded), dists float, ascending (distance, id).  Asynchronous on the index's stream
+ * unless sync != 0 (stats != NULL also synchronises the local search to read its counters). */
+EPS_API int eps_search_batch_sharded(eps_shard_group* g, eps_index* ix, int64_t id_base, const float* d_queries, int64_t nq,
+                                     int64_t k, const eps_filter_node* filter, int64_t n_filter, int64_t* d_out_ids,
+                                     float* d_out_dists, eps_stats* stats, int sync);
+
 /* engine::Normalize (db/vector.cpp:60-69) for nq host vectors in place, on device. */
 EPS_API int eps_normalize(int device, float* host_vectors, int64_t nq, int64_t dim);
 

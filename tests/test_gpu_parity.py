@@ -487,3 +487,76 @@ def test_cta_pair_tensor_core_variant_matches(vdb):
         del os.environ["EPS_TC_2CTA"]
     assert np.array_equal(got, want) and np.allclose(gd, wd)
     ix.close()
+
+
+# ---- row shards with the exchange inside the library (NCCL bound at run time) -----------------------------------
+def test_sharded_search_single_rank_group(vdb):
+    """eps_search_batch_sharded with a world of one rank (all a 1-GPU box can form): local search -> global ids ->
+    ncclAllGather -> merge kernel must equal the plain search shifted by id_base."""
+    import torch
+    from vectordb_b200.sharded import ShardGroup
+    n, d, nq, k, base = 30000, 48, 64, 10, 1_000_000
+    X, Q = gen(n, d, 31), gen(nq, d, 32)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.config(500, 500, force_brute=True)
+    want, wd, _, _ = ix.search(Q, k)
+    g = ShardGroup(ShardGroup.unique_id(), 0, 1, 0)
+    tq = torch.from_numpy(Q).cuda()
+    oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    g.search(ix, base, tq.data_ptr(), nq, k, oi.data_ptr(), od.data_ptr())
+    assert np.array_equal(oi.cpu().numpy(), want + base)
+    assert np.allclose(od.cpu().numpy(), wd, rtol=1e-6)
+    g.close()
+    ix.close()
+
+
+def _shard_worker(rank, world, uid_path, out_path):
+    import os
+    import time
+    import numpy as np
+    import torch
+    import vectordb_b200
+    from helpers import gen
+    from vectordb_b200.sharded import ShardGroup, shard_range
+    torch.cuda.set_device(rank)
+    if rank == 0:
+        with open(uid_path + ".tmp", "wb") as f:
+            f.write(ShardGroup.unique_id())
+        os.replace(uid_path + ".tmp", uid_path)
+    while not os.path.exists(uid_path):
+        time.sleep(0.05)
+    uid = open(uid_path, "rb").read()
+    n, d, nq, k = 40000, 48, 64, 10
+    X, Q = gen(n, d, 41), gen(nq, d, 42)
+    lo, hi = shard_range(n, rank, world)
+    ix = vectordb_b200.Index("l2", d, host_vectors=X[lo:hi], device=rank)
+    ix.sync_rows(hi - lo)
+    ix.config(500, 500, force_brute=True)
+    g = ShardGroup(uid, rank, world, rank)
+    tq = torch.from_numpy(Q).cuda()
+    oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    g.search(ix, lo, tq.data_ptr(), nq, k, oi.data_ptr(), od.data_ptr())
+    np.savez(out_path % rank, ids=oi.cpu().numpy(), dists=od.cpu().numpy())
+    g.close()
+    ix.close()
+
+
+def test_sharded_search_two_ranks(vdb, tmp_path):
+    """World of two ranks on two GPUs (skipped on a 1-GPU box): merged results on both ranks equal the exact top-k
+    of the whole table."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    uid_path, out_path = str(tmp_path / "uid.bin"), str(tmp_path / "out%d.npz")
+    mp.spawn(_shard_worker, args=(2, uid_path, out_path), nprocs=2, join=True)
+    X, Q = gen(40000, 48, 41), gen(64, 48, 42)
+    truth = exact_topk(X, Q, 10)
+    for r in range(2):
+        got = np.load(out_path % r)
+        assert recall(got["ids"], truth, 10) > 0.999
+        assert np.all(np.diff(got["dists"], axis=1) >= 0)
+    assert np.array_equal(np.load(out_path % 0)["ids"], np.load(out_path % 1)["ids"])

@@ -110,8 +110,8 @@ __global__ void finalize_keys_kernel(const unsigned long long* __restrict__ topk
 // k-way merge of n_shards sorted lists per query (ids are GLOBAL int64).  One CTA per query, bitonic
 // sort of the (ordered-distance, id) pairs in shared memory.
 __global__ void merge_shards_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dists, int n_shards,
-                                    int nq, int k, int np, int64_t* __restrict__ out_ids,
-                                    float* __restrict__ out_dists) {
+                                    int nq, int k, int np, int64_t id_stride, int64_t dist_stride,
+                                    int64_t* __restrict__ out_ids, float* __restrict__ out_dists) {
   extern __shared__ __align__(16) unsigned char ms_smem[];
   int64_t* sid = reinterpret_cast<int64_t*>(ms_smem);
   uint32_t* sod = reinterpret_cast<uint32_t*>(sid + np);
@@ -122,9 +122,9 @@ __global__ void merge_shards_kernel(const int64_t* __restrict__ ids, const float
     uint32_t od = 0xffffffffu;
     if (i < n) {
       const int s = i / k, j = i % k;
-      const int64_t src = (static_cast<int64_t>(s) * nq + q) * k + j;
-      id = ids[src];
-      od = id >= 0 ? float_to_ordered(dists[src]) : 0xffffffffu;
+      const int64_t within = static_cast<int64_t>(q) * k + j;  // shard s: ids + s*id_stride, dists + s*dist_stride
+      id = ids[static_cast<int64_t>(s) * id_stride + within];
+      od = id >= 0 ? float_to_ordered(dists[static_cast<int64_t>(s) * dist_stride + within]) : 0xffffffffu;
       if (id < 0) id = INT64_MAX;
     } else {
       id = INT64_MAX;
@@ -181,7 +181,9 @@ int finalize_keys(Index* ix, const unsigned long long* d_topk, int64_t nq, int64
 }
 
 int merge_shards(int device, cudaStream_t stream, const int64_t* d_ids, const float* d_dists, int64_t n_shards,
-                 int64_t nq, int64_t k, int64_t* d_out_ids, float* d_out_dists) {
+                 int64_t nq, int64_t k, int64_t* d_out_ids, float* d_out_dists, int64_t id_stride, int64_t dist_stride) {
+  if (id_stride <= 0) id_stride = nq * k;      // dense [n_shards x nq x k] layout
+  if (dist_stride <= 0) dist_stride = nq * k;
   EPS_CUDA(cudaSetDevice(device));
   const int np = next_pow2(static_cast<int>(n_shards * k));
   const size_t smem = static_cast<size_t>(np) * 12;
@@ -190,7 +192,7 @@ int merge_shards(int device, cudaStream_t stream, const int64_t* d_ids, const fl
     EPS_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   merge_shards_kernel<<<static_cast<unsigned>(nq), 256, smem, stream>>>(d_ids, d_dists, static_cast<int>(n_shards),
                                                                         static_cast<int>(nq), static_cast<int>(k), np,
-                                                                        d_out_ids, d_out_dists);
+                                                                        id_stride, dist_stride, d_out_ids, d_out_dists);
   EPS_CUDA(cudaGetLastError());
   return EPS_OK;
 }

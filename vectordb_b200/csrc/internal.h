@@ -131,8 +131,10 @@ int finalize_graph(Index* ix, unsigned long long* d_queue, int64_t nq, int64_t L
 // Brute-force results: first min(valid, limit_cap) keys -> ids/dists/counts.
 int finalize_keys(Index* ix, const unsigned long long* d_topk, int64_t nq, int64_t k, int64_t limit, int64_t cap,
                   int64_t* d_ids, float* d_dists, int64_t* d_counts);
+// shard s reads ids + s*id_stride and dists + s*dist_stride (elements; <= 0: the dense [n_shards x nq x k] layout)
 int merge_shards(int device, cudaStream_t stream, const int64_t* d_ids, const float* d_dists, int64_t n_shards,
-                 int64_t nq, int64_t k, int64_t* d_out_ids, float* d_out_dists);
+                 int64_t nq, int64_t k, int64_t* d_out_ids, float* d_out_dists, int64_t id_stride = 0,
+                 int64_t dist_stride = 0);
 
 // ---- build.cu ------------------------------------------------------------------------------
 int build_graph(Index* ix, int64_t n, const eps_build_params* params);

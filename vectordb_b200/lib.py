@@ -9,7 +9,7 @@ _LIB = None
 EXPORTS = [
     "eps_index_create", "eps_index_destroy", "eps_index_sync_rows", "eps_index_adopt_device_rows",
     "eps_index_set_graph", "eps_index_build", "eps_index_get_graph", "eps_index_set_deleted", "eps_index_set_attrs",
-    "eps_index_config", "eps_index_set_coarse", "eps_index_set_search_width", "eps_index_set_graph_tuning", "eps_search_batch", "eps_search_batch_device", "eps_merge_shards_device", "eps_normalize",
+    "eps_index_config", "eps_index_set_coarse", "eps_index_set_search_width", "eps_index_set_graph_tuning", "eps_search_batch", "eps_search_batch_device", "eps_merge_shards_device", "eps_shard_unique_id", "eps_shard_group_create", "eps_shard_group_destroy", "eps_search_batch_sharded", "eps_normalize",
     "eps_pair_distances", "eps_index_stream", "eps_last_error", "eps_version", "eps_device_count",
 ]
 
@@ -78,6 +78,11 @@ def load_library():
     L.eps_search_batch_device.argtypes = [vp, vp, i64, i64, vp, i64, vp, vp, vp, vp, i32]
     L.eps_merge_shards_device.argtypes = [i32, vp, vp, i64, i64, i64, vp, vp]
     L.eps_normalize.argtypes = [i32, vp, i64, i64]
+    L.eps_shard_unique_id.argtypes = [vp]
+    L.eps_shard_group_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32]
+    L.eps_shard_group_destroy.argtypes = [vp]
+    L.eps_shard_group_destroy.restype = None
+    L.eps_search_batch_sharded.argtypes = [vp, vp, i64, vp, i64, i64, vp, i64, vp, vp, vp, i32]
     L.eps_pair_distances.argtypes = [i32, i32, vp, vp, i64, i64, vp]
     L.eps_index_stream.argtypes = [vp]
     L.eps_index_stream.restype = vp

@@ -60,3 +60,37 @@ def exchange_and_merge(local_ids, local_dists, base, k, dist, merge_fn):
     dist.all_gather_into_tensor(all_i.view(-1), gids.view(-1))
     dist.all_gather_into_tensor(all_d.view(-1), local_dists.contiguous().view(-1))
     return merge_fn(all_i, all_d, k)
+
+
+class ShardGroup:
+    """ctypes mirror of eps_shard_group (include/epsilla_b200.h): the NCCL exchange INSIDE the library.
+    `unique_id` (128 bytes from ShardGroup.unique_id() on one rank) must reach every rank by host means."""
+
+    def __init__(self, unique_id, rank, world, device):
+        import ctypes as C
+        from .lib import check, load_library
+        self.L = load_library()
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        h = C.c_void_p()
+        check(self.L.eps_shard_group_create(C.byref(h), buf, int(rank), int(world), int(device)))
+        self.h, self.rank, self.world = h, rank, world
+
+    @staticmethod
+    def unique_id():
+        import ctypes as C
+        from .lib import check, load_library
+        buf = (C.c_char * 128)()
+        check(load_library().eps_shard_unique_id(buf))
+        return bytes(buf)
+
+    def search(self, index, id_base, d_queries_ptr, nq, k, d_out_ids_ptr, d_out_dists_ptr, sync=True):
+        """Every rank: same device-resident query batch, own shard index -> merged GLOBAL top-k on every rank."""
+        import ctypes as C
+        from .lib import check
+        check(self.L.eps_search_batch_sharded(self.h, index.h, int(id_base), C.c_void_p(d_queries_ptr), int(nq), int(k), None, 0,
+                                              C.c_void_p(d_out_ids_ptr), C.c_void_p(d_out_dists_ptr), None, int(bool(sync))))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.eps_shard_group_destroy(self.h)
+            self.h = None
