@@ -46,8 +46,11 @@ typedef struct eps_index eps_index;
  * (-1: no field, -2: the "@distance" pseudo-field, query/expr/expr_evaluator.cpp:143-145).
  * node_type / value_type carry the reference enum ordinals (expr_types.hpp:11-48, :67-74).
  * Nodes are in the parser's order: children before parents, root last
- * (db/execution/vec_search_executor.cpp:848).  String / IN / LIKE / NEARBY nodes are rejected with
- * EPS_ERR_UNSUPPORTED (out of scope: string / regex / geo work). */
+ * (db/execution/vec_search_executor.cpp:848).
+ * Strings: a StringAttr node carries the string-column index in field_offset, a StringConst node the literal's
+ * dictionary code in int_value (-1 if the literal is not in the dictionary); string EQ / NE compare codes; the
+ * caller lowers `x IN (a, b, ..)` to `x = a OR x = b ..` (integration/epsilla_b200_dropin.cpp does).  LIKE, string
+ * concatenation and NEARBY nodes are rejected with EPS_ERR_UNSUPPORTED (regex / geo work, out of scope). */
 typedef struct eps_filter_node {
   int64_t node_type;
   int64_t value_type;
@@ -106,6 +109,12 @@ EPS_API void eps_index_destroy(eps_index* ix);
  * (db/execution/vec_search_executor.cpp:839). */
 EPS_API int eps_index_sync_rows(eps_index* ix, int64_t n_rows_now);
 
+/* The device copy of the vector table ([rows x dim] float, row-major) and how many rows are mirrored; lets a second
+ * index (the graph build that TableMVP::Rebuild runs beside the live executors, db/table_mvp.cpp:143-195) work on
+ * the same HBM rows through eps_index_adopt_device_rows instead of uploading the table again. */
+EPS_API const float* eps_index_device_rows(eps_index* ix);
+EPS_API int64_t eps_index_rows(eps_index* ix);
+
 /* Use an already device-resident [n_rows x dim] float table (not copied, not owned). */
 EPS_API int eps_index_adopt_device_rows(eps_index* ix, const float* d_vectors, int64_t n_rows);
 
@@ -130,6 +139,12 @@ EPS_API int eps_index_set_deleted(eps_index* ix, const uint8_t* bitset, int64_t 
 /* TableSegmentMVP::attribute_table_ with row stride primitive_offset_
  * (db/table_segment_mvp.cpp:99, query/expr/expr_evaluator.cpp:61-102). */
 EPS_API int eps_index_set_attrs(eps_index* ix, const char* attribute_table, int64_t row_stride, int64_t n_rows);
+
+/* String columns (TableSegmentMVP::var_len_attr_table_[column], db/table_segment_mvp.hpp:82) are mirrored as
+ * DICTIONARY CODES: the caller keeps one string -> int32 dictionary per table and appends the codes of new rows
+ * [first_row, first_row + count) here; filter nodes then compare codes (query/expr/expr_evaluator.cpp:110-125,
+ * :176-190: StrEvaluate / string EQ, NE / IN).  column = the field's index in var_len_attr_table_ (< 8). */
+EPS_API int eps_index_set_string_codes(eps_index* ix, int column, int64_t first_row, const int32_t* codes, int64_t count);
 
 /* Executor parameters snapshotted at construction (db/table_mvp.cpp:83-87): L_master, L_local
  * (config.hpp MasterQueueSize / LocalQueueSize), prefilter_enabled_.  force_brute != 0 makes every

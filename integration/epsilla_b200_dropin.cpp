@@ -22,12 +22,14 @@
 //
 // Scope limits, reported as a non-OK Status instead of silently computing on the CPU: sparse-vector fields
 // and string / IN / LIKE / NEARBY filter nodes.
-#include <chrono>
+#include <cstdlib>
+#include <atomic>
 #include <condition_variable>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "db/ann_graph_segment.hpp"
@@ -60,22 +62,43 @@ struct Mirror {
   struct Pending {
     const float* query;
     size_t limit;
+    const std::vector<eps_filter_node>* nodes;  // lowered filter program (empty = none); equal programs share a launch
     int64_t* ids;
     double* dists;
     int64_t count = 0;
     int rc = EPS_OK;
+    std::string err;  // eps_last_error() is thread-local: the leader copies the text for its followers
     bool done = false;
   };
   std::mutex qmu;
   std::condition_variable qcv;
   std::vector<Pending*> waiting;
   bool leader_active = false;
+  uint64_t calls = 0, launches = 0;  // Search() calls served / eps_search_batch launches made (coalescing evidence)
+  // String columns are mirrored as dictionary codes: one string -> code dictionary per table,
+  // rows encoded incrementally (append-only) the first time a filter reads the column.
+  std::unordered_map<std::string, int32_t> dict;
+  std::vector<int64_t> str_rows;  // per string column: rows whose codes are on the device
   ~Mirror() {
     if (ix) eps_index_destroy(ix);
   }
 };
 
-using Key = std::tuple<const float*, const ANNGraphSegment*, int64_t, int64_t, bool, int>;
+// The executor's own ann_index_ member owns the mirror: it is an ALIAS of the mirror's shared_ptr that still points
+// at the graph.  std::get_deleter on that alias reaches the control block's deleter, which remembers the mirror.
+struct MirrorDeleter {
+  Mirror* self = nullptr;
+  void operator()(Mirror* p) const { delete p; }
+};
+static Mirror* MirrorOf(const std::shared_ptr<ANNGraphSegment>& alias) {
+  const MirrorDeleter* d = std::get_deleter<MirrorDeleter>(alias);
+  return d ? d->self : nullptr;
+}
+
+// process-wide coalescing evidence (tests): Search() calls served and eps_search_batch launches made
+static std::atomic<int64_t> g_calls{0}, g_launches{0};
+
+using Key = std::tuple<const float*, const ANNGraphSegment*, int64_t, int64_t, bool, int, int>;
 static std::mutex g_mu;
 static std::map<Key, std::weak_ptr<Mirror>> g_mirrors;
 
@@ -95,56 +118,81 @@ static Status Fail(const char* what) {
   return Status(DB_UNEXPECTED_ERROR, std::string("epsilla_b200: ") + what + ": " + eps_last_error());
 }
 
-// Leader/follower batch former.  The first caller becomes the leader: it waits a short window for followers,
-// then serves every queued request with the same limit in one eps_search_batch call (other limits in further
-// calls), copies each result out and wakes the followers.  Requests keep their per-call semantics (one query,
+static bool SameProgram(const std::vector<eps_filter_node>& a, const std::vector<eps_filter_node>& b) {
+  return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(eps_filter_node)) == 0);
+}
+
+// Leader/follower batch former.  The first caller becomes the leader and serves, in ONE eps_search_batch call,
+// every request queued at that moment with the same limit and the same filter program; requests that arrive
+// while a launch is in flight queue up and form the next batch, so a lone caller never waits and concurrent
+// callers are batched by the device's own service time.  Requests keep their per-call semantics (one query,
 // own result arrays); only the launch is shared.
-static int SearchCoalesced(Mirror* m, const float* query, size_t limit, int64_t* ids, double* dists, int64_t* count) {
+static int SearchCoalesced(Mirror* m, const float* query, size_t limit, const std::vector<eps_filter_node>& nodes, int64_t* ids,
+                           double* dists, int64_t* count, std::string* err) {
   Mirror::Pending me;
-  me.query = query; me.limit = limit; me.ids = ids; me.dists = dists;
+  me.query = query; me.limit = limit; me.nodes = &nodes; me.ids = ids; me.dists = dists;
   std::unique_lock<std::mutex> q(m->qmu);
   m->waiting.push_back(&me);
   if (m->leader_active) {
     m->qcv.wait(q, [&] { return me.done || !m->leader_active; });
-    if (me.done) { *count = me.count; return me.rc; }
+    if (me.done) { *count = me.count; *err = me.err; return me.rc; }
     // the leader left before taking this request: fall through and lead
   }
   m->leader_active = true;
   while (!me.done) {
-    m->qcv.wait_for(q, std::chrono::microseconds(100));  // batching window
     std::vector<Mirror::Pending*> batch;
     std::vector<Mirror::Pending*> rest;
-    const size_t lim = m->waiting.front()->limit;
-    for (auto* p : m->waiting) (p->limit == lim ? batch : rest).push_back(p);
+    Mirror::Pending* head = m->waiting.front();
+    for (auto* p : m->waiting) ((p->limit == head->limit && SameProgram(*p->nodes, *head->nodes)) ? batch : rest).push_back(p);
     m->waiting.swap(rest);
     q.unlock();
+    const size_t lim = head->limit;
     const int64_t nq = static_cast<int64_t>(batch.size());
-    std::vector<float> qbuf(static_cast<size_t>(nq) * m->dim);
-    for (int64_t i = 0; i < nq; ++i) std::memcpy(qbuf.data() + i * m->dim, batch[i]->query, sizeof(float) * m->dim);
-    std::vector<int64_t> oi(static_cast<size_t>(nq) * lim), oc(static_cast<size_t>(nq));
-    std::vector<double> od(static_cast<size_t>(nq) * lim);
     int rc;
-    {
-      std::lock_guard<std::mutex> lk(m->mu);  // the index itself is single-threaded
-      rc = eps_search_batch(m->ix, qbuf.data(), nq, static_cast<int64_t>(lim), nullptr, 0, oi.data(), od.data(), oc.data(), nullptr);
+    std::string text;
+    if (nq == 1) {  // no copy through staging buffers for a lone request
+      std::lock_guard<std::mutex> lk(m->mu);
+      rc = eps_search_batch(m->ix, head->query, 1, static_cast<int64_t>(lim), head->nodes->empty() ? nullptr : head->nodes->data(),
+                            static_cast<int64_t>(head->nodes->size()), head->ids, head->dists, &head->count, nullptr);
+      if (rc != EPS_OK) text = eps_last_error();
+      ++m->launches; ++g_launches;
+    } else {
+      std::vector<float> qbuf(static_cast<size_t>(nq) * m->dim);
+      for (int64_t i = 0; i < nq; ++i) std::memcpy(qbuf.data() + i * m->dim, batch[i]->query, sizeof(float) * m->dim);
+      std::vector<int64_t> oi(static_cast<size_t>(nq) * lim), oc(static_cast<size_t>(nq));
+      std::vector<double> od(static_cast<size_t>(nq) * lim);
+      {
+        std::lock_guard<std::mutex> lk(m->mu);  // the index itself is single-threaded
+        rc = eps_search_batch(m->ix, qbuf.data(), nq, static_cast<int64_t>(lim), head->nodes->empty() ? nullptr : head->nodes->data(),
+                              static_cast<int64_t>(head->nodes->size()), oi.data(), od.data(), oc.data(), nullptr);
+        if (rc != EPS_OK) text = eps_last_error();
+        ++m->launches; ++g_launches;
+      }
+      if (rc == EPS_OK) {
+        for (int64_t i = 0; i < nq; ++i) {
+          batch[i]->count = oc[i];
+          std::memcpy(batch[i]->ids, oi.data() + i * lim, sizeof(int64_t) * lim);
+          std::memcpy(batch[i]->dists, od.data() + i * lim, sizeof(double) * lim);
+        }
+      }
     }
     q.lock();
-    for (int64_t i = 0; i < nq; ++i) {
-      auto* p = batch[i];
-      p->rc = rc;
-      if (rc == EPS_OK) {
-        p->count = oc[i];
-        std::memcpy(p->ids, oi.data() + i * lim, sizeof(int64_t) * lim);
-        std::memcpy(p->dists, od.data() + i * lim, sizeof(double) * lim);
-      }
-      p->done = true;
-    }
+    m->calls += static_cast<uint64_t>(nq);
+    g_calls += nq;
+    for (auto* p : batch) { p->rc = rc; p->err = text; p->done = true; }
     m->qcv.notify_all();
   }
   m->leader_active = false;
   m->qcv.notify_all();  // a queued follower (if any) takes over as leader
   *count = me.count;
+  *err = me.err;
   return me.rc;
+}
+
+// Device ordinal of the mirrors: EPSILLA_B200_DEVICE (the reference has no GPU setting to read it from).
+static int DeviceOrdinal() {
+  static const int dev = [] { const char* e = std::getenv("EPSILLA_B200_DEVICE"); return e ? std::atoi(e) : 0; }();
+  return dev;
 }
 
 }  // namespace b200
@@ -184,14 +232,15 @@ VecSearchExecutor::VecSearchExecutor(const int64_t dimension, const int64_t star
     return;
   }
   float* table = std::get<DenseVectorColumnDataContainer>(vector_column);
-  b200::Key key(table, ann_index.get(), L_master, L_local, prefilter_enabled, metric);
+  b200::Key key(table, ann_index.get(), L_master, L_local, prefilter_enabled, metric, num_threads);
   std::shared_ptr<b200::Mirror> m;
   {
     std::lock_guard<std::mutex> lk(b200::g_mu);
     auto it = b200::g_mirrors.find(key);
     if (it != b200::g_mirrors.end()) m = it->second.lock();
     if (!m) {
-      m = std::make_shared<b200::Mirror>();
+      b200::Mirror* raw = new b200::Mirror();
+      m = std::shared_ptr<b200::Mirror>(raw, b200::MirrorDeleter{raw});
       m->ann = ann_index;
       m->metric = metric;
       m->dim = dimension;
@@ -207,50 +256,121 @@ VecSearchExecutor::VecSearchExecutor(const int64_t dimension, const int64_t star
   }
   // the executor's own ann_index_ owns the mirror (aliasing constructor) and still points at the graph
   ann_index_ = std::shared_ptr<ANNGraphSegment>(m, ann_index.get());
-  init_ids_[0] = reinterpret_cast<int64_t>(m.get());
 }
 
 Status VecSearchExecutor::Search(const VectorPtr query_data, vectordb::engine::TableSegmentMVP* table_segment,
                                  const size_t limit, std::vector<vectordb::query::expr::ExprNodePtr>& filter_nodes,
                                  int64_t& result_size) {
   result_size = 0;
-  auto* m = reinterpret_cast<b200::Mirror*>(init_ids_[0]);
+  b200::Mirror* m = b200::MirrorOf(ann_index_);
   if (m == nullptr || !std::holds_alternative<DenseVectorPtr>(query_data))
     return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: sparse-vector search is out of scope of the GPU path");
   std::unique_lock<std::mutex> lk(m->mu);
   const int64_t total = table_segment->record_number_;  // snapshot (:839)
   if (m->ix == nullptr) {
     m->capacity = static_cast<int64_t>(table_segment->size_limit_);
-    if (eps_index_create(&m->ix, m->metric, m->dim, m->host_vectors, m->capacity, 0) != EPS_OK) return b200::Fail("create");
+    if (eps_index_create(&m->ix, m->metric, m->dim, m->host_vectors, m->capacity, b200::DeviceOrdinal()) != EPS_OK) return b200::Fail("create");
     if (eps_index_sync_rows(m->ix, std::max<int64_t>(total, total_indexed_vector_)) != EPS_OK) return b200::Fail("sync_rows");
     if (total_indexed_vector_ > 0 &&
         eps_index_set_graph(m->ix, total_indexed_vector_, m->offsets, m->nbrs, m->nav) != EPS_OK)
       return b200::Fail("set_graph");
     if (eps_index_config(m->ix, m->L_master, m->L_local, m->prefilter ? 1 : 0, 0) != EPS_OK) return b200::Fail("config");
+    // IntraQueryThreads (config.hpp:18, default 4): 1 = the sequential order, > 1 = that many candidates expanded
+    // concurrently (the reference's parallel mode is itself not a pure function of its inputs)
+    const int width = num_threads_ >= 8 ? 8 : num_threads_ >= 4 ? 4 : num_threads_ >= 2 ? 2 : 1;
+    if (eps_index_set_search_width(m->ix, width) != EPS_OK) return b200::Fail("search_width");
   }
   if (eps_index_sync_rows(m->ix, total) != EPS_OK) return b200::Fail("sync_rows");
   ConcurrentBitset& deleted = *(table_segment->deleted_);  // (:840)
   if (eps_index_set_deleted(m->ix, deleted.data(), (total + 7) / 8) != EPS_OK) return b200::Fail("set_deleted");
 
-  // filter nodes -> PODs, field names resolved through the segment's offset map (:841-848)
-  std::vector<eps_filter_node> nodes(filter_nodes.size());
-  for (size_t i = 0; i < filter_nodes.size(); ++i) {
-    const auto& s = *filter_nodes[i];
-    eps_filter_node& d = nodes[i];
-    d.node_type = static_cast<int64_t>(s.node_type);
-    d.value_type = static_cast<int64_t>(s.value_type);
-    d.left = static_cast<int64_t>(s.left);
-    d.right = static_cast<int64_t>(s.right);
-    d.int_value = s.int_value;
-    d.double_value = s.double_value;
-    d.bool_value = s.bool_value ? 1 : 0;
-    d.field_offset = -1;
-    if (!s.field_name.empty()) {
-      if (s.field_name == "@distance") d.field_offset = -2;
-      else {
-        auto it = table_segment->field_name_mem_offset_map_.find(s.field_name);
-        if (it != table_segment->field_name_mem_offset_map_.end()) d.field_offset = static_cast<int64_t>(it->second);
+  // filter nodes -> PODs (:841-848): field names resolved through the segment's offset map; string work happens
+  // here, on the host — new rows of the string columns a filter reads are dictionary-encoded and appended to the
+  // device mirror, literals become codes, `x IN (a, b, ..)` becomes `x = a OR x = b ..`.
+  std::vector<eps_filter_node> nodes;
+  {
+    using query::expr::NodeType;
+    using query::expr::ValueType;
+    for (const auto& np : filter_nodes) {
+      if (np->node_type != NodeType::StringAttr) continue;
+      auto it = table_segment->field_name_mem_offset_map_.find(np->field_name);
+      if (it == table_segment->field_name_mem_offset_map_.end()) continue;
+      const size_t col = it->second;
+      if (col >= 8 || col >= table_segment->var_len_attr_table_.size())
+        return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: more than 8 string columns are out of scope of the GPU path");
+      if (m->str_rows.size() <= col) m->str_rows.resize(col + 1, 0);
+      if (m->str_rows[col] < total) {
+        std::vector<int32_t> codes;
+        codes.reserve(static_cast<size_t>(total - m->str_rows[col]));
+        auto& column = table_segment->var_len_attr_table_[col];
+        for (int64_t r = m->str_rows[col]; r < total; ++r) {
+          const std::string* sv = std::get_if<std::string>(&column[r]);
+          auto ins = m->dict.emplace(sv ? *sv : std::string(), static_cast<int32_t>(m->dict.size()));
+          codes.push_back(ins.first->second);
+        }
+        if (eps_index_set_string_codes(m->ix, static_cast<int>(col), m->str_rows[col], codes.data(), static_cast<int64_t>(codes.size())) != EPS_OK)
+          return b200::Fail("set_string_codes");
+        m->str_rows[col] = total;
       }
+    }
+    std::vector<int64_t> remap(filter_nodes.size(), -1);  // parser index -> index of the POD holding the node's value
+    auto pod = [](NodeType t, ValueType v) {
+      eps_filter_node d;
+      std::memset(&d, 0, sizeof(d));
+      d.node_type = static_cast<int64_t>(t);
+      d.value_type = static_cast<int64_t>(v);
+      d.left = d.right = -1;
+      d.field_offset = -1;
+      return d;
+    };
+    for (size_t i = 0; i < filter_nodes.size(); ++i) {
+      const auto& sn = *filter_nodes[i];
+      if (sn.node_type == NodeType::IN) {  // expr_evaluator.cpp:176-185: last argument is the attribute
+        const size_t len = sn.arguments.size();
+        if (len < 2) return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: malformed IN node");
+        const int64_t attr = remap[sn.arguments[len - 1]];
+        int64_t acc = -1;
+        for (size_t j = 0; j + 1 < len; ++j) {
+          eps_filter_node eq = pod(NodeType::EQ, ValueType::BOOL);
+          eq.left = attr;
+          eq.right = remap[sn.arguments[j]];
+          nodes.push_back(eq);
+          const int64_t eq_at = static_cast<int64_t>(nodes.size()) - 1;
+          if (acc < 0) { acc = eq_at; continue; }
+          eps_filter_node o = pod(NodeType::OR, ValueType::BOOL);
+          o.left = acc;
+          o.right = eq_at;
+          nodes.push_back(o);
+          acc = static_cast<int64_t>(nodes.size()) - 1;
+        }
+        remap[i] = acc;
+        continue;
+      }
+      if (sn.node_type == NodeType::Add && sn.value_type == ValueType::STRING)
+        return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: string concatenation in filters is out of scope of the GPU path");
+      eps_filter_node d = pod(sn.node_type, sn.value_type);
+      const bool unary = sn.node_type == NodeType::NOT;
+      const bool leaf = sn.node_type <= NodeType::GeoPointAttr;
+      if (!leaf) {
+        d.left = sn.left < filter_nodes.size() ? remap[sn.left] : -1;
+        d.right = (!unary && sn.right < filter_nodes.size()) ? remap[sn.right] : -1;
+      }
+      d.int_value = sn.int_value;
+      d.double_value = sn.double_value;
+      d.bool_value = sn.bool_value ? 1 : 0;
+      if (sn.node_type == NodeType::StringConst) {
+        auto it = m->dict.find(sn.str_value);
+        d.int_value = it == m->dict.end() ? -1 : it->second;  // a literal no row carries equals nothing
+      }
+      if (!sn.field_name.empty()) {
+        if (sn.field_name == "@distance") d.field_offset = -2;
+        else {
+          auto it = table_segment->field_name_mem_offset_map_.find(sn.field_name);
+          if (it != table_segment->field_name_mem_offset_map_.end()) d.field_offset = static_cast<int64_t>(it->second);
+        }
+      }
+      nodes.push_back(d);
+      remap[i] = static_cast<int64_t>(nodes.size()) - 1;
     }
   }
   if (!nodes.empty() && (m->attr_rows != total || m->attr_ptr != table_segment->attribute_table_)) {
@@ -264,19 +384,15 @@ Status VecSearchExecutor::Search(const VectorPtr query_data, vectordb::engine::T
     distance_.resize(limit);
   }
   int64_t count = 0;
-  int rc;
-  if (nodes.empty()) {
-    // hand the request to the mirror's batch former: release the mirror lock while queued so that the other
-    // executors of the pool (engine/db/execution/executor_pool.hpp) can join the same batch
-    lk.unlock();
-    rc = b200::SearchCoalesced(m, std::get<DenseVectorPtr>(query_data), limit, search_result_.data(), distance_.data(), &count);
-    lk.lock();
-  } else {
-    rc = eps_search_batch(m->ix, std::get<DenseVectorPtr>(query_data), 1, static_cast<int64_t>(limit), nodes.data(),
-                          static_cast<int64_t>(nodes.size()), search_result_.data(), distance_.data(), &count, nullptr);
-  }
-  if (rc == EPS_ERR_UNSUPPORTED) return Status(NOT_IMPLEMENTED_ERROR, std::string("epsilla_b200: ") + eps_last_error());
-  if (rc != EPS_OK) return b200::Fail("search");
+  std::string err;
+  // hand the request to the mirror's batch former: release the mirror lock while queued so that the other
+  // executors of the pool (engine/db/execution/executor_pool.hpp) can join the same batch
+  lk.unlock();
+  const int rc = b200::SearchCoalesced(m, std::get<DenseVectorPtr>(query_data), limit, nodes, search_result_.data(), distance_.data(),
+                                       &count, &err);
+  lk.lock();
+  if (rc == EPS_ERR_UNSUPPORTED) return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: " + err);
+  if (rc != EPS_OK) return Status(DB_UNEXPECTED_ERROR, "epsilla_b200: search: " + err);
   result_size = count;
   return Status::OK();  // (:934)
 }
@@ -298,8 +414,30 @@ void ANNGraphSegment::BuildFromVectorTable(VectorColumnData vector_column, int64
     if (ix) eps_index_destroy(ix);
     throw std::runtime_error(msg);
   };
-  if (eps_index_create(&ix, metric, dim, std::get<DenseVectorColumnDataContainer>(vector_column), n, 0) != EPS_OK) die("create");
-  if (eps_index_sync_rows(ix, n) != EPS_OK) die("sync_rows");
+  // Rows already mirrored for an executor of this table are reused in place (no second upload of the table): the
+  // build index adopts the device rows of a live mirror, which stays pinned until the build is done.
+  float* table = std::get<DenseVectorColumnDataContainer>(vector_column);
+  std::shared_ptr<b200::Mirror> donor;
+  {
+    std::lock_guard<std::mutex> lk(b200::g_mu);
+    for (auto& kv : b200::g_mirrors) {
+      if (std::get<0>(kv.first) != table) continue;
+      auto sp = kv.second.lock();
+      if (sp && sp->ix && sp->capacity >= n) { donor = sp; break; }
+    }
+  }
+  const float* d_rows = nullptr;
+  if (donor) {
+    std::lock_guard<std::mutex> lk(donor->mu);
+    if (eps_index_sync_rows(donor->ix, std::max<int64_t>(n, eps_index_rows(donor->ix))) == EPS_OK) d_rows = eps_index_device_rows(donor->ix);
+  }
+  if (d_rows) {
+    if (eps_index_create(&ix, metric, dim, nullptr, n, b200::DeviceOrdinal()) != EPS_OK) die("create");
+    if (eps_index_adopt_device_rows(ix, d_rows, n) != EPS_OK) die("adopt_device_rows");
+  } else {
+    if (eps_index_create(&ix, metric, dim, table, n, b200::DeviceOrdinal()) != EPS_OK) die("create");
+    if (eps_index_sync_rows(ix, n) != EPS_OK) die("sync_rows");
+  }
   if (eps_index_build(ix, n, nullptr) != EPS_OK) die("build");
   int64_t ni = 0, ne = 0, nav = 0;
   if (eps_index_get_graph(ix, &ni, &ne, nullptr, nullptr, &nav) != EPS_OK) die("get_graph");
@@ -317,3 +455,9 @@ void ANNGraphSegment::BuildFromVectorTable(VectorColumnData vector_column, int64
 
 }  // namespace engine
 }  // namespace vectordb
+
+// Coalescing counters of this process (Search() calls served, launches made), for the integration tests.
+extern "C" __attribute__((visibility("default"))) void eps_dropin_counters(int64_t* calls, int64_t* launches) {
+  if (calls) *calls = vectordb::engine::b200::g_calls.load();
+  if (launches) *launches = vectordb::engine::b200::g_launches.load();
+}

@@ -20,7 +20,7 @@ REF_SO = os.path.join(OUT, "libepsilla_ref.so")
 
 METRIC = {"l2": 1, "euclidean": 1, "cosine": 2, "cos": 2, "ip": 3, "dot": 3, "dot_product": 3}
 # meta::FieldType (engine/db/catalog/meta_types.hpp:19-45)
-FIELD_TYPE = {"int1": 1, "int2": 2, "int4": 3, "int8": 4, "float": 10, "double": 11, "bool": 30}
+FIELD_TYPE = {"int1": 1, "int2": 2, "int4": 3, "int8": 4, "float": 10, "double": 11, "string": 20, "bool": 30}
 FIELD_NP = {"int1": np.int8, "int2": np.int16, "int4": np.int32, "int8": np.int64, "float": np.float32,
             "double": np.float64, "bool": np.uint8}
 
@@ -169,6 +169,7 @@ class Ref:
         L.ref_attr_offset.restype = C.c_int64
         L.ref_attr_offset.argtypes = [C.c_void_p, C.c_char_p]
         L.ref_set_rows.argtypes = [C.c_void_p, C.c_int64]
+        L.ref_set_string.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_char_p]
         L.ref_set_deleted.argtypes = [C.c_void_p, C.c_int64, C.c_int]
         L.ref_build.argtypes = [C.c_void_p, C.c_int64, C.c_int]
         L.ref_set_graph.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
@@ -230,6 +231,12 @@ class Ref:
         raw = self.attrs.reshape(self.capacity, self.stride)
         sz = values.dtype.itemsize
         raw[:values.shape[0], off:off + sz] = values.view(np.uint8).reshape(-1, sz)
+
+    def set_string_column(self, name, values, first_row=0):
+        """String attribute column (var_len_attr_table_): values[i] -> row first_row + i."""
+        for i, v in enumerate(values):
+            if self.L.ref_set_string(self.h, name.encode(), first_row + i, str(v).encode()) != 0:
+                raise ValueError("no string field %r" % name)
 
     def set_rows(self, vectors):
         vectors = np.ascontiguousarray(vectors, np.float32)

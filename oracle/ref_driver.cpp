@@ -95,6 +95,14 @@ int64_t ref_attr_offset(void* h, const char* name) {
   auto it = m.find(name);
   return it == m.end() ? -1 : static_cast<int64_t>(it->second);
 }
+// String attribute of one row (TableSegmentMVP::var_len_attr_table_[column][row], table_segment_mvp.hpp:82).
+int ref_set_string(void* h, const char* name, int64_t row, const char* value) {
+  auto* c = static_cast<RefCtx*>(h);
+  auto it = c->seg->field_name_mem_offset_map_.find(name);
+  if (it == c->seg->field_name_mem_offset_map_.end() || it->second >= c->seg->var_len_attr_table_.size()) return -1;
+  c->seg->var_len_attr_table_[it->second][row] = std::string(value);
+  return 0;
+}
 void ref_set_rows(void* h, int64_t n) { static_cast<RefCtx*>(h)->seg->record_number_ = n; }
 void ref_set_deleted(void* h, int64_t id, int flag) {
   auto* c = static_cast<RefCtx*>(h);

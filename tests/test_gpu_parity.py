@@ -560,3 +560,34 @@ def test_sharded_search_two_ranks(vdb, tmp_path):
         assert recall(got["ids"], truth, 10) > 0.999
         assert np.all(np.diff(got["dists"], axis=1) >= 0)
     assert np.array_equal(np.load(out_path % 0)["ids"], np.load(out_path % 1)["ids"])
+
+
+def test_string_codes_filter_through_c_abi(vdb):
+    """f4 at the C ABI: dictionary-coded string column + StringAttr / StringConst / EQ / NE / OR nodes."""
+    n, d, nq, k = 20000, 32, 16, 10
+    X, Q = gen(n, d, 81), gen(nq, d, 82)
+    codes = (np.arange(n) % 7).astype(np.int32)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.config(500, 500, force_brute=True)
+    ix.set_string_codes(0, 0, codes[:12000])
+    ix.set_string_codes(0, 12000, codes[12000:])   # appended rows
+    S_ATTR, S_CONST, EQ, NE, OR = 9, 2, 21, 24, 26
+    def prog(op, lits):
+        nodes = [[S_ATTR, 0, -1, -1, 0, 0, 0, 0]]
+        acc = None
+        for c in lits:
+            nodes.append([S_CONST, 0, -1, -1, c, 0, 0, -1])
+            nodes.append([op, 3, 0, len(nodes) - 1, 0, 0, 0, -1])
+            if acc is not None:
+                nodes.append([OR, 3, acc, len(nodes) - 1, 0, 0, 0, -1])
+            acc = len(nodes) - 1
+        return np.array(nodes, np.int64)
+    for op, lits, keep in ((EQ, [3], codes == 3), (NE, [3], codes != 3), (EQ, [1, 5, -1], np.isin(codes, [1, 5]))):
+        ids, ds, cnt, _ = ix.search(Q, k, filter_nodes=prog(op, lits))
+        rows = np.nonzero(keep)[0]
+        want = rows[exact_topk(X[rows], Q, k)]
+        assert np.all(cnt == k) and recall(ids, want, k) == 1.0
+    with pytest.raises(Exception):   # a column that is not mirrored for every row must be refused, not read out of bounds
+        ix.search(Q, k, filter_nodes=np.array([[S_ATTR, 0, -1, -1, 0, 0, 0, 1], [S_CONST, 0, -1, -1, 0, 0, 0, -1], [EQ, 3, 0, 1, 0, 0, 0, -1]], np.int64))
+    ix.close()

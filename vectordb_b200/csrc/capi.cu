@@ -49,7 +49,7 @@ static int check_device(int device) {
 int lower_filter(const eps_filter_node* nodes, int64_t n, FilterProg* out) {
   std::memset(out, 0, sizeof(*out));
   if (n <= 0 || nodes == nullptr) return EPS_OK;
-  if (n > kMaxFilterNodes) return fail(EPS_ERR_UNSUPPORTED, "filter has more than 48 nodes");
+  if (n > kMaxFilterNodes) return fail(EPS_ERR_UNSUPPORTED, "filter has more than 64 nodes");
   for (int64_t i = 0; i < n; ++i) {
     const eps_filter_node& s = nodes[i];
     FNode& d = out->nodes[i];
@@ -58,6 +58,11 @@ int lower_filter(const eps_filter_node* nodes, int64_t n, FilterProg* out) {
       case NT_IntConst: d.value = static_cast<double>(s.int_value); break;
       case NT_DoubleConst: d.value = s.double_value; break;
       case NT_BoolConst: d.value = s.bool_value ? 1.0 : 0.0; break;
+      case NT_StringConst: d.value = static_cast<double>(s.int_value); break;  // dictionary code of the literal
+      case NT_StringAttr:
+        if (s.field_offset < 0 || s.field_offset >= kMaxStringCols)
+          return fail(EPS_ERR_INVALID_ARGUMENT, "string attribute node needs a string-column index in [0, 8)");
+        break;
       case NT_Int1Attr: case NT_Int2Attr: case NT_Int4Attr: case NT_Int8Attr: case NT_BoolAttr:
         if (s.field_offset < 0) return fail(EPS_ERR_INVALID_ARGUMENT, "filter attribute node without a field offset");
         break;
@@ -76,7 +81,7 @@ int lower_filter(const eps_filter_node* nodes, int64_t n, FilterProg* out) {
         break;
       default:
         return fail(EPS_ERR_UNSUPPORTED,
-                    "filter node type " + std::to_string(t) + " (string / IN / LIKE / geo / aggregation) is out of scope");
+                    "filter node type " + std::to_string(t) + " (LIKE / IN not lowered to OR / geo / aggregation) is out of scope");
     }
     d.type = static_cast<int16_t>(t);
     d.vtype = static_cast<int16_t>(s.value_type);
@@ -88,7 +93,7 @@ int lower_filter(const eps_filter_node* nodes, int64_t n, FilterProg* out) {
   const FNode& r = out->nodes[n - 1];
   const bool cmp = r.type == NT_GT || r.type == NT_GTE || r.type == NT_LT || r.type == NT_LTE;
   const bool eq = (r.type == NT_EQ || r.type == NT_NE) && out->nodes[r.left].vtype != VT_BOOL &&
-                  out->nodes[r.left].vtype != VT_STRING;
+                  out->nodes[r.left].vtype != VT_STRING;  // string EQ goes through StrEvaluate: no distance
   out->root_uses_dist = (out->uses_distance && (cmp || eq)) ? 1 : 0;
   return EPS_OK;
 }
@@ -153,6 +158,13 @@ static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t 
         case NT_Int4Attr: case NT_FloatAttr: width = 4; break;
         case NT_Int8Attr: case NT_DoubleAttr: width = 8; break;
         default: break;
+      }
+      if (nd.type == NT_StringAttr) {
+        const eps::StrCol& sc = ix->str_cols[nd.field_offset];
+        if (!sc.d_codes || sc.rows < ix->n_rows)
+          return fail(EPS_ERR_INVALID_ARGUMENT, "filter reads a string column whose dictionary codes are not mirrored for every row");
+        h_prog.str_col[nd.field_offset] = sc.d_codes;
+        continue;
       }
       if (width == 0 || nd.field_offset < 0) continue;  // constants, operators, the @distance pseudo-field
       if (!ix->d_attrs) return fail(EPS_ERR_INVALID_ARGUMENT, "filter reads attributes but eps_index_set_attrs was not called");
@@ -276,6 +288,7 @@ void eps_index_destroy(eps_index* h) {
   if (ix->owns_vectors && ix->d_vectors) cudaFree(ix->d_vectors);
   if (ix->d_deleted) cudaFree(ix->d_deleted);
   if (ix->d_attrs) cudaFree(ix->d_attrs);
+  for (auto& sc : ix->str_cols) if (sc.d_codes) cudaFree(sc.d_codes);
   eps::DevBuf* bufs[] = {&ix->s_queries, &ix->s_dist, &ix->s_topk, &ix->s_topk2, &ix->s_pass, &ix->s_filter,
                          &ix->s_visited, &ix->s_queue, &ix->s_tail, &ix->s_out_ids, &ix->s_out_dists,
                          &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist, &ix->s_xnorm, &ix->s_qnorm, &ix->s_coarse, &ix->s_thr, &ix->s_cand, &ix->s_cand_cnt, &ix->s_bf16, &ix->s_qbf16};
@@ -378,36 +391,110 @@ int eps_index_get_graph(eps_index* h, int64_t* n_indexed, int64_t* n_edges, int6
   return EPS_OK;
 }
 
+// The reference flips single bits of deleted_ (db/table_segment_mvp.cpp:429-449) and exposes no dirty tracking, so
+// the mirror keeps a host shadow of what it uploaded and ships only the byte span that changed since the last
+// call (nothing at all in the common case): a 64-bit-word compare of N/8 bytes instead of an N/8-byte H2D copy.
 int eps_index_set_deleted(eps_index* h, const uint8_t* bitset, int64_t nbytes) {
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
   EPS_TRY(eps::check_device(ix->device));
-  if (!bitset || nbytes <= 0) { ix->any_deleted = false; return EPS_OK; }
-  if (nbytes > ix->deleted_bytes) {
-    if (ix->d_deleted) cudaFree(ix->d_deleted);
-    ix->d_deleted = nullptr;
-    EPS_CUDA(cudaMalloc(&ix->d_deleted, static_cast<size_t>(nbytes)));
+  if (!bitset || nbytes <= 0) { ix->any_deleted = false; ix->deleted_bytes = 0; ix->h_deleted.clear(); return EPS_OK; }
+  int64_t lo = 0, hi = nbytes;  // dirty span [lo, hi)
+  const bool same_geometry = ix->d_deleted && static_cast<int64_t>(ix->h_deleted.size()) == nbytes && nbytes <= ix->deleted_cap;
+  if (same_geometry) {
+    const uint8_t* old = ix->h_deleted.data();
+    int64_t w = 0;
+    const int64_t nw = nbytes / 8;
+    while (w < nw && reinterpret_cast<const uint64_t*>(old)[w] == reinterpret_cast<const uint64_t*>(bitset)[w]) ++w;
+    lo = w * 8;
+    while (lo < nbytes && old[lo] == bitset[lo]) ++lo;
+    if (lo == nbytes) return EPS_OK;  // unchanged
+    hi = nbytes;
+    while (hi > lo && old[hi - 1] == bitset[hi - 1]) --hi;
+  } else {
+    if (nbytes > ix->deleted_cap) {
+      if (ix->d_deleted) cudaFree(ix->d_deleted);
+      ix->d_deleted = nullptr;
+      // room for the whole table so that growth of record_number_ never reallocates
+      const int64_t cap = std::max<int64_t>(nbytes, (ix->capacity + 7) / 8 + 8);
+      EPS_CUDA(cudaMalloc(&ix->d_deleted, static_cast<size_t>(cap)));
+      ix->deleted_cap = cap;
+    }
+    ix->h_deleted.assign(static_cast<size_t>(nbytes), 0);
+    ix->any_deleted = false;
   }
-  ix->deleted_bytes = nbytes;
-  EPS_CUDA(cudaMemcpyAsync(ix->d_deleted, bitset, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice, ix->stream));
+  EPS_CUDA(cudaMemcpyAsync(ix->d_deleted + lo, bitset + lo, static_cast<size_t>(hi - lo), cudaMemcpyHostToDevice, ix->stream));
   EPS_CUDA(cudaStreamSynchronize(ix->stream));
-  bool any = false;
-  for (int64_t i = 0; i < nbytes && !any; ++i) any = bitset[i] != 0;
-  ix->any_deleted = any;
+  std::memcpy(ix->h_deleted.data() + lo, bitset + lo, static_cast<size_t>(hi - lo));
+  ix->deleted_bytes = nbytes;
+  if (!ix->any_deleted) {
+    bool any = false;
+    for (int64_t i = lo; i < hi && !any; ++i) any = bitset[i] != 0;
+    ix->any_deleted = any;  // sticky: un-deleting every row only costs a bitmap test per row
+  }
   return EPS_OK;
 }
 
+// attribute_table_ is append-only for rows below record_number_ (an upsert deletes the old row and appends a new
+// one, db/table_segment_mvp.cpp:564-587): the same table grown to more rows uploads only the new rows.
 int eps_index_set_attrs(eps_index* h, const char* table, int64_t stride, int64_t n_rows) {
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
   EPS_TRY(eps::check_device(ix->device));
-  if (ix->d_attrs) { cudaFree(ix->d_attrs); ix->d_attrs = nullptr; }
+  if (!table || stride <= 0 || n_rows <= 0) {
+    if (ix->d_attrs) { cudaFree(ix->d_attrs); ix->d_attrs = nullptr; }
+    ix->attr_stride = stride; ix->attr_rows = 0; ix->attr_cap_rows = 0; ix->attr_src = nullptr;
+    return EPS_OK;
+  }
+  int64_t first = 0;
+  if (ix->d_attrs && ix->attr_src == table && ix->attr_stride == stride && n_rows >= ix->attr_rows && n_rows <= ix->attr_cap_rows) {
+    first = ix->attr_rows;  // append
+  } else {
+    if (ix->d_attrs) { cudaFree(ix->d_attrs); ix->d_attrs = nullptr; }
+    const int64_t cap = std::max<int64_t>(n_rows, ix->capacity);
+    EPS_CUDA(cudaMalloc(&ix->d_attrs, static_cast<size_t>(stride) * cap));
+    ix->attr_cap_rows = cap;
+  }
   ix->attr_stride = stride;
+  ix->attr_src = table;
+  if (n_rows > first) {
+    EPS_CUDA(cudaMemcpyAsync(ix->d_attrs + first * stride, table + first * stride, static_cast<size_t>(stride) * (n_rows - first),
+                             cudaMemcpyHostToDevice, ix->stream));
+    EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  }
   ix->attr_rows = n_rows;
-  if (!table || stride <= 0 || n_rows <= 0) return EPS_OK;
-  EPS_CUDA(cudaMalloc(&ix->d_attrs, static_cast<size_t>(stride) * n_rows));
-  EPS_CUDA(cudaMemcpyAsync(ix->d_attrs, table, static_cast<size_t>(stride) * n_rows, cudaMemcpyHostToDevice, ix->stream));
-  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  return EPS_OK;
+}
+
+// Dictionary codes of rows [first_row, first_row + count) of string column `column` (TableSegmentMVP::
+// var_len_attr_table_[column], db/table_segment_mvp.hpp:82).  Rows are append-only like the attribute table.
+int eps_index_set_string_codes(eps_index* h, int column, int64_t first_row, const int32_t* codes, int64_t count) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  if (column < 0 || column >= eps::kMaxStringCols) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "string column index must be in [0, 8)");
+  if (first_row < 0 || count < 0 || (count > 0 && !codes)) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "bad row range / null codes");
+  EPS_TRY(eps::check_device(ix->device));
+  eps::StrCol& sc = ix->str_cols[column];
+  if (first_row > sc.rows) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "string codes must be appended without gaps");
+  const int64_t need = first_row + count;
+  if (need > sc.cap) {
+    const int64_t cap = std::max<int64_t>(need, std::max<int64_t>(ix->capacity, 2 * sc.cap));
+    int32_t* fresh = nullptr;
+    EPS_CUDA(cudaMalloc(&fresh, static_cast<size_t>(cap) * 4));
+    if (sc.d_codes && sc.rows > 0) {
+      cudaError_t e = cudaMemcpyAsync(fresh, sc.d_codes, static_cast<size_t>(sc.rows) * 4, cudaMemcpyDeviceToDevice, ix->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+      if (e != cudaSuccess) { cudaFree(fresh); return eps::fail(EPS_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    if (sc.d_codes) cudaFree(sc.d_codes);
+    sc.d_codes = fresh;
+    sc.cap = cap;
+  }
+  if (count > 0) {
+    EPS_CUDA(cudaMemcpyAsync(sc.d_codes + first_row, codes, static_cast<size_t>(count) * 4, cudaMemcpyHostToDevice, ix->stream));
+    EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  }
+  sc.rows = std::max(sc.rows, need);
   return EPS_OK;
 }
 
@@ -564,6 +651,9 @@ int eps_index_set_coarse(eps_index* h, int mode) {
   ix->coarse_mode = mode;
   return EPS_OK;
 }
+
+const float* eps_index_device_rows(eps_index* h) { return h ? reinterpret_cast<Index*>(h)->d_vectors : nullptr; }
+int64_t eps_index_rows(eps_index* h) { return h ? reinterpret_cast<Index*>(h)->n_rows : 0; }
 
 void* eps_index_stream(eps_index* h) { return h ? reinterpret_cast<Index*>(h)->stream : nullptr; }
 

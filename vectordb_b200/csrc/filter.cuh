@@ -7,6 +7,10 @@
 //  * NOT / AND / OR / bool-typed EQ,NE evaluate their children through the two-argument overload,
 //    i.e. with distance 0 (:166-168,:184,:204-211) — "@distance" only sees the real distance when
 //    the ROOT is a numeric comparison.  Hence one effective distance per evaluation (root_dist()).
+//  * strings: a string column is mirrored as DICTIONARY CODES (int32 per row, one dictionary per
+//    table so codes compare across columns); StringAttr reads the row's code, StringConst carries the literal's
+//    code (-1: literal absent from the dictionary, equal to no row), and string EQ / NE (:186-190) compare codes.
+//    IN (:176-185) is lowered by the caller to an OR of EQs; LIKE and string concatenation stay out of scope.
 // The parser emits children before parents, so one forward pass over the node array evaluates the
 // tree without recursion.
 #pragma once
@@ -14,7 +18,8 @@
 
 namespace eps {
 
-constexpr int kMaxFilterNodes = 48;
+constexpr int kMaxFilterNodes = 64;
+constexpr int kMaxStringCols = 8;
 
 enum NodeType : int {  // query/expr/expr_types.hpp:11-48
   NT_Invalid, NT_IntConst, NT_StringConst, NT_DoubleConst, NT_BoolConst, NT_Int1Attr, NT_Int2Attr, NT_Int4Attr,
@@ -39,6 +44,7 @@ struct FilterProg {
   int uses_distance;  // any node reads "@distance"
   int root_uses_dist; // root is a numeric comparison (the only place the real distance is visible)
   int pad;
+  const int32_t* str_col[kMaxStringCols];  // device columns of dictionary codes (filled when the program is lowered)
   FNode nodes[kMaxFilterNodes];
 };
 
@@ -58,7 +64,9 @@ __device__ __forceinline__ bool filter_eval(const FilterProg& p, const char* __r
     bool b = false;
     switch (nd.type) {
       case NT_IntConst:
+      case NT_StringConst:
       case NT_DoubleConst: v = nd.value; break;
+      case NT_StringAttr: v = static_cast<double>(p.str_col[nd.field_offset][row]); break;
       case NT_BoolConst: b = nd.value != 0.0; break;
       case NT_Int1Attr: v = static_cast<double>(*reinterpret_cast<const int8_t*>(base + nd.field_offset)); break;
       case NT_Int2Attr: { int16_t x; memcpy(&x, base + nd.field_offset, 2); v = static_cast<double>(x); break; }

@@ -24,6 +24,12 @@ struct DevBuf {
   T* as() { return static_cast<T*>(p); }
 };
 
+// Device mirror of one string column as dictionary codes (filter.cuh).
+struct StrCol {
+  int32_t* d_codes = nullptr;
+  int64_t rows = 0, cap = 0;
+};
+
 struct Index {
   int device = 0;
   int metric = EPS_METRIC_L2;
@@ -49,10 +55,15 @@ struct Index {
   // segment mirrors
   uint8_t* d_deleted = nullptr;
   int64_t deleted_bytes = 0;
+  int64_t deleted_cap = 0;
+  std::vector<uint8_t> h_deleted;  // host shadow of the uploaded bitset (dirty-span detection)
   bool any_deleted = false;
   char* d_attrs = nullptr;
   int64_t attr_stride = 0;
   int64_t attr_rows = 0;
+  int64_t attr_cap_rows = 0;
+  const char* attr_src = nullptr;  // host table the mirror was filled from (append detection)
+  StrCol str_cols[kMaxStringCols];
 
   // executor parameters
   int64_t L_master = 500, L_local = 500;

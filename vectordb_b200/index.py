@@ -99,6 +99,11 @@ class Index:
         t = np.ascontiguousarray(table_bytes, np.uint8)
         check(self.L.eps_index_set_attrs(self.h, _p(t), int(stride), int(n_rows)))
 
+    def set_string_codes(self, column, first_row, codes):
+        """Append the dictionary codes of rows [first_row, first_row + len(codes)) of string column `column`."""
+        c = np.ascontiguousarray(codes, np.int32)
+        check(self.L.eps_index_set_string_codes(self.h, int(column), int(first_row), _p(c), c.size))
+
     def config(self, L_master=500, L_local=None, prefilter=False, force_brute=False):
         L_local = L_master if L_local is None else L_local
         check(self.L.eps_index_config(self.h, int(L_master), int(L_local), int(bool(prefilter)), int(bool(force_brute))))

@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 EXPORTS = [
-    "eps_index_create", "eps_index_destroy", "eps_index_sync_rows", "eps_index_adopt_device_rows",
-    "eps_index_set_graph", "eps_index_build", "eps_index_get_graph", "eps_index_set_deleted", "eps_index_set_attrs",
+    "eps_index_create", "eps_index_destroy", "eps_index_sync_rows", "eps_index_adopt_device_rows", "eps_index_device_rows", "eps_index_rows",
+    "eps_index_set_graph", "eps_index_build", "eps_index_get_graph", "eps_index_set_deleted", "eps_index_set_attrs", "eps_index_set_string_codes",
     "eps_index_config", "eps_index_set_coarse", "eps_index_set_search_width", "eps_index_set_graph_tuning", "eps_search_batch", "eps_search_batch_device", "eps_merge_shards_device", "eps_shard_unique_id", "eps_shard_group_create", "eps_shard_group_destroy", "eps_search_batch_sharded", "eps_normalize",
     "eps_pair_distances", "eps_index_stream", "eps_last_error", "eps_version", "eps_device_count",
 ]
@@ -65,11 +65,16 @@ def load_library():
     L.eps_index_destroy.restype = None
     L.eps_index_sync_rows.argtypes = [vp, i64]
     L.eps_index_adopt_device_rows.argtypes = [vp, vp, i64]
+    L.eps_index_device_rows.argtypes = [vp]
+    L.eps_index_device_rows.restype = vp
+    L.eps_index_rows.argtypes = [vp]
+    L.eps_index_rows.restype = i64
     L.eps_index_set_graph.argtypes = [vp, i64, vp, vp, i64]
     L.eps_index_build.argtypes = [vp, i64, vp]
     L.eps_index_get_graph.argtypes = [vp, vp, vp, vp, vp, vp]
     L.eps_index_set_deleted.argtypes = [vp, vp, i64]
     L.eps_index_set_attrs.argtypes = [vp, vp, i64, i64]
+    L.eps_index_set_string_codes.argtypes = [vp, i32, i64, vp, i64]
     L.eps_index_config.argtypes = [vp, i64, i64, i32, i32]
     L.eps_index_set_coarse.argtypes = [vp, i32]
     L.eps_index_set_search_width.argtypes = [vp, i32]
