@@ -470,25 +470,6 @@ def test_large_batch_top100_with_filter(vdb, port):
     ix.close()
 
 
-def test_cta_pair_tensor_core_variant_matches(vdb):
-    """EPS_TC_2CTA=1 selects the tcgen05 cta_group::2 kernel (two CTAs per 256x256 tile): same answers."""
-    import os
-    n, d, nq, k = 400000, 64, 256, 10
-    X, Q = gen(n, d, 601), gen(nq, d, 602)
-    ix = vdb.Index("l2", d, host_vectors=X)
-    ix.sync_rows(n)
-    ix.config(500, 500, force_brute=True)
-    ix.set_coarse("bf16")
-    want, wd, _, _ = ix.search(Q, k)
-    os.environ["EPS_TC_2CTA"] = "1"
-    try:
-        got, gd, _, _ = ix.search(Q, k)
-    finally:
-        del os.environ["EPS_TC_2CTA"]
-    assert np.array_equal(got, want) and np.allclose(gd, wd)
-    ix.close()
-
-
 # ---- row shards with the exchange inside the library (NCCL bound at run time) -----------------------------------
 def test_sharded_search_single_rank_group(vdb):
     """eps_search_batch_sharded with a world of one rank (all a 1-GPU box can form): local search -> global ids ->

@@ -528,12 +528,11 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     // it; it also seeds the per-query running threshold.  Later tensor-core chunks filter against that
     // threshold inside the epilogue (no distance tile leaves the SM) and only the few survivors are merged.
     const bool fused = use_tc && c0 > 0;
-    // tensor-core mode: a small first chunk of 32 K rows (it pays the distance-tile round trip; expected survivors of
-    // the next launch: k' * 512K / 32K = 16 k' << candidate capacity), then fused launches that grow
-    // as the thresholds tighten (expected survivors per query ~ k' * rows_in_launch / rows_seen_so_far)
+    // tensor-core mode: a first chunk of only 4 K rows pays the distance-tile round trip (16 MB tile, 4 M keys to
+    // select from), then fused launches grow 8x at a time as the thresholds tighten: expected survivors per query
+    // of a launch ~ k' * rows_in_launch / rows_seen_so_far = 8 k' << candidate capacity
     int64_t want_rows = chunk;
-    if (use_tc) want_rows = fused ? std::min<int64_t>(std::max<int64_t>(4 * c0, 512 * 1024), 4 * 1024 * 1024)
-                                  : std::min<int64_t>(chunk, 32 * 1024);
+    if (use_tc) want_rows = fused ? std::min<int64_t>(8 * c0, 4 * 1024 * 1024) : std::min<int64_t>(chunk, 4 * 1024);
     const int64_t cn = std::min(want_rows, n - c0);
     SelectArgs a;
     a.ldd = chunk; a.row_base = row_start + c0; a.nsplit = nsplit; a.k = static_cast<int>(k); a.state = state;

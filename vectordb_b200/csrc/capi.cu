@@ -125,6 +125,14 @@ int normalize_rows_device(cudaStream_t s, float* d, int64_t n, int64_t dim) {
   return EPS_OK;
 }
 
+__global__ void narrow_ids_kernel(const int64_t* __restrict__ in, int64_t n, int64_t limit, int32_t* __restrict__ out,
+                                  int* __restrict__ bad) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int64_t v = in[i];
+  if (v < 0 || v >= limit) { *bad = 1; out[i] = 0; } else out[i] = static_cast<int32_t>(v);
+}
+
 static void free_graph(Index* ix) {
   if (ix->d_offsets) cudaFree(ix->d_offsets);
   if (ix->d_nbrs) cudaFree(ix->d_nbrs);
@@ -350,16 +358,29 @@ int eps_index_set_graph(eps_index* h, int64_t n_indexed, const int64_t* offsets,
   for (int64_t i = 0; i < n_indexed; ++i)
     if (offsets[i + 1] < offsets[i]) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "offset table is not monotonic");
   if (e > 0 && !nbrs) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null neighbor list");
-  std::vector<int32_t> nb32(static_cast<size_t>(e > 0 ? e : 1));
-  for (int64_t i = 0; i < e; ++i) {
-    if (nbrs[i] < 0 || nbrs[i] >= n_indexed) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "neighbor id out of range");
-    nb32[i] = static_cast<int32_t>(nbrs[i]);
-  }
   EPS_CUDA(cudaMalloc(&ix->d_offsets, (static_cast<size_t>(n_indexed) + 1) * 8));
-  EPS_CUDA(cudaMalloc(&ix->d_nbrs, nb32.size() * 4));
+  EPS_CUDA(cudaMalloc(&ix->d_nbrs, static_cast<size_t>(e > 0 ? e : 1) * 4));
   EPS_CUDA(cudaMemcpyAsync(ix->d_offsets, offsets, (static_cast<size_t>(n_indexed) + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
-  EPS_CUDA(cudaMemcpyAsync(ix->d_nbrs, nb32.data(), nb32.size() * 4, cudaMemcpyHostToDevice, ix->stream));
-  EPS_CUDA(cudaStreamSynchronize(ix->stream));
+  // neighbour ids: int64 in the reference CSR, int32 on the device — narrowed and range-checked by a kernel over
+  // 64M-edge chunks (a host loop over 4e8 edges costs seconds)
+  {
+    const int64_t chunk = 64ll << 20;
+    eps::DevBuf stage, flag;
+    EPS_TRY(stage.reserve(static_cast<size_t>(std::min<int64_t>(chunk, std::max<int64_t>(e, 1))) * 8));
+    EPS_TRY(flag.reserve(4));
+    EPS_CUDA(cudaMemsetAsync(flag.p, 0, 4, ix->stream));
+    for (int64_t c0 = 0; c0 < e; c0 += chunk) {
+      const int64_t cn = std::min(chunk, e - c0);
+      EPS_CUDA(cudaMemcpyAsync(stage.p, nbrs + c0, static_cast<size_t>(cn) * 8, cudaMemcpyHostToDevice, ix->stream));
+      eps::narrow_ids_kernel<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, ix->stream>>>(stage.as<int64_t>(), cn, n_indexed,
+                                                                                              ix->d_nbrs + c0, flag.as<int>());
+      EPS_CUDA(cudaGetLastError());
+      EPS_CUDA(cudaStreamSynchronize(ix->stream));  // the staging buffer is reused by the next chunk
+    }
+    int bad = 0;
+    EPS_CUDA(cudaMemcpy(&bad, flag.p, 4, cudaMemcpyDeviceToHost));
+    if (bad) { eps::free_graph(ix); return eps::fail(EPS_ERR_INVALID_ARGUMENT, "neighbor id out of range"); }
+  }
   ix->n_indexed = n_indexed;
   ix->n_edges = e;
   ix->nav = nav;

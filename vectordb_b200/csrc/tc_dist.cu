@@ -57,12 +57,7 @@ struct TcArgs {
   const uint32_t* pass;         // deleted / static-filter bitmap relative to pass_base (may be null)
   int64_t pass_base;
   int cand_cap;
-  // EPS_TC_DEBUG (developer timing aid, results are garbage when set): bit 0 = stop issuing TMA loads after the
-  // first ring fill, bit 1 = skip the MMAs, bit 2 = skip the epilogue's TMEM reads.  Brackets which of the three
-  // engines bounds the kernel (tools/tc_limiter.py).
-  int debug;
-  int epi_pipelined;  // EPS_TC_EPI: 1 = overlap the TMEM read of the next chunk with the compare of this one (measured: no
-                      // gain), 2 = experimental branch-light compare (epi_chunk_fast); 0 / unset = the validated default
+  int epi_fast;  // EPS_TC_EPI=2 (read once per process): branch-light compare of the fused selection (epi_chunk_fast)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
@@ -181,7 +176,7 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
   return r;
 }
-// EXPERIMENTAL (EPS_TC_EPI=2, fused mode only; not yet measured on the GPU): branch-light form of the fused
+// EPS_TC_EPI=2 (fused mode only): branch-light form of the fused
 // selection.  The thresholds of the chunk come from true LDS loads issued before the TMEM wait, all 32 compares
 // fold into four predicate chains and ONE rarely-taken branch per chunk guards the candidate push (epi_chunk
 // branches once per 4 elements behind a dependent generic load: 64 serialised round trips per 128x256 tile).
@@ -252,7 +247,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
       const float th = a.thr[i];
       c = a.metric == EPS_METRIC_L2 ? th - qn : (a.metric == EPS_METRIC_COSINE ? th - 1.0f : th);
     }
-    thr_s[i] = a.debug ? -INFINITY : c;
+    thr_s[i] = c;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -272,7 +267,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
-            if ((a.debug & 1) && it >= kTcStages) { mbar_arrive(full0 + 8 * s); continue; }
             mbar_expect_tx(full0 + 8 * s, kTcStageBytes);
             const uint32_t sa = stage0 + s * kTcStageBytes;
             tma_load_2d(sa, &tmA, kb * a.kb_elems, row0, full0 + 8 * s);
@@ -301,7 +295,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
             const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + kTcABytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // 4 MMAs per 128-byte block: K = 8 tf32 / 16 bf16 = 32 bytes = +2 (16-B units)
-              if (a.debug & 2) break;
               if (bf16) umma_issue<true>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
               else umma_issue<false>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
             }
@@ -331,9 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lq) << 16) + acc * kTcBN;
         const int qbase = qt * kTcBN;
-        if (a.debug & 4) {
-          // timing aid: leave the accumulator unread
-        } else if (a.epi_pipelined == 2 && a.D == nullptr) {
+        if (a.epi_fast && a.D == nullptr) {
           const uint32_t thr_addr = smem_u32(thr_s);
 #pragma unroll 1
           for (int c = 0; c < kTcBN / 32; ++c) {
@@ -344,20 +335,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
             for (int j4 = 0; j4 < 8; ++j4) ct[j4] = lds128(thr_addr + static_cast<uint32_t>(qbase + c * 32 + 4 * j4) * 4u);
             tmem_ld_wait();
             epi_chunk_fast(a, v, ct, qbase + c * 32, row_ok, xn, row_abs, qn_s);
-          }
-        } else if (a.epi_pipelined) {
-          // software-pipelined: the TMEM read of chunk c+1 is in flight while chunk c is compared (two register
-          // sets; TMEM reads are 64 B/clk per SM, so an un-overlapped load + compare per chunk is epilogue-bound)
-          uint32_t va[32], vb[32];
-          tmem_ld32(va, taddr0);
-#pragma unroll 1
-          for (int c = 0; c < kTcBN / 32; c += 2) {
-            tmem_ld_wait();
-            tmem_ld32(vb, taddr0 + (c + 1) * 32);
-            epi_chunk(a, va, qbase + c * 32, row_ok, xn, i, row_abs, thr_s, qn_s);
-            tmem_ld_wait();
-            if (c + 2 < kTcBN / 32) tmem_ld32(va, taddr0 + (c + 2) * 32);
-            epi_chunk(a, vb, qbase + (c + 1) * 32, row_ok, xn, i, row_abs, thr_s, qn_s);
           }
         } else {
 #pragma unroll 1
@@ -377,228 +354,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster work on one 256-row x 256-query tile.  Each CTA
-// stages its own 128 rows of the table and HALF of the query block (128 queries) — the tensor cores of both SMs
-// read both halves — so the query-side operand traffic per flop halves and a stage shrinks to 32 KB (6 stages).
-// CTA 0 (leader) issues the MMAs; TMA completions of both CTAs land on the leader's "full" barrier
-// (cp.async.bulk.tensor ... cta_group::2, barrier address with the peer bit cleared); tcgen05.commit multicasts
-// the "stage free" and "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive remotely on
-// the leader's "accumulator drained" barrier.  Same epilogue, same results as tc_dist_kernel.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kTc2Stages = 6;
-constexpr int kTc2HalfB = kTcBBytes / 2;                 // 16 KB: 128 queries x 128 B
-constexpr int kTc2StageBytes = kTcABytes + kTc2HalfB;    // 32 KB
-constexpr int kTc2Smem = kTc2Stages * kTc2StageBytes + 1024 + 8192 + 256;
-constexpr uint32_t kPeerMask = 0xFEFFFFFFu;              // clears the CTA-rank bit of a shared::cluster address
-
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar & kPeerMask)
-      : "memory");
-}
-template <bool BF16>
-__device__ __forceinline__ void umma_issue_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if (BF16) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    return;
-  }
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-tc_dist_kernel_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a) {
-  extern __shared__ unsigned char tc_smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-  float* qn_s = reinterpret_cast<float*>(base + kTc2Stages * kTc2StageBytes);
-  float* thr_s = qn_s + 1024;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kTc2Stages * kTc2StageBytes + 8192);
-  // bars[0..5] full (leader's are used), [6..11] empty, [12..13] tmem_full, [14..15] tmem_empty (leader's), slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 6), tfull0 = smem_u32(bars + 12), tempty0 = smem_u32(bars + 14);
-  const uint32_t stage0 = smem_u32(base);
-  uint32_t rank;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (a.dim + a.kb_elems - 1) / a.kb_elems;
-  const int n_pair_tiles = (a.n_row_tiles + 1) >> 1;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kTc2Stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(tfull0 + 8 * t, 1); mbar_init(tempty0 + 8 * t, 8); }
-    mbar_fence_init();
-  }
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-    const float qn = (a.metric == EPS_METRIC_L2 && i < a.nq) ? a.qnorm[i] : 0.f;
-    qn_s[i] = qn;
-    float c = -INFINITY;
-    if (a.D == nullptr && i < a.nq) {
-      const float th = a.thr[i];
-      c = a.metric == EPS_METRIC_L2 ? th - qn : (a.metric == EPS_METRIC_COSINE ? th - 1.0f : th);
-    }
-    thr_s[i] = c;
-  }
-  __syncthreads();
-  cluster_sync_all();  // both CTAs' barriers exist before any remote arrival
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  cluster_sync_all();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-      uint32_t it = 0;
-      for (int pt = pair; pt < n_pair_tiles; pt += npairs) {
-        const int row0 = static_cast<int>(a.row_start) + pt * 2 * kTcBM + static_cast<int>(rank) * kTcBM;
-        for (int qt = 0; qt < a.n_q_tiles; ++qt) {
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const uint32_t s = it % kTc2Stages, ph = (it / kTc2Stages) & 1;
-            mbar_wait(empty0 + 8 * s, ph ^ 1);
-            if (leader) mbar_expect_tx(full0 + 8 * s, 2 * kTc2StageBytes);  // bytes of BOTH CTAs land on this barrier
-            const uint32_t sa = stage0 + s * kTc2StageBytes;
-            tma_load_2d_2sm(sa, &tmA, kb * a.kb_elems, row0, full0 + 8 * s);
-            tma_load_2d_2sm(sa + kTcABytes, &tmB, kb * a.kb_elems, qt * kTcBN + static_cast<int>(rank) * (kTcBN / 2), full0 + 8 * s);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (leader && lane == 0) {
-      const bool bf16 = a.kb_elems == 64;
-      // M = 256 (two CTAs x 128 rows), N = 256
-      uint32_t idesc = bf16 ? umma_idesc(1u) : umma_idesc(2u);
-      idesc = (idesc & ~(0x1Fu << 24)) | ((256u >> 4) << 24);
-      uint32_t it = 0, tc = 0;
-      for (int pt = pair; pt < n_pair_tiles; pt += npairs) {
-        for (int qt = 0; qt < a.n_q_tiles; ++qt, ++tc) {
-          const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
-          mbar_wait(tempty0 + 8 * acc, aph ^ 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t tmem_d = tmem_base + acc * kTcBN;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const uint32_t s = it % kTc2Stages, ph = (it / kTc2Stages) & 1;
-            mbar_wait(full0 + 8 * s, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = stage0 + s * kTc2StageBytes;
-            const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + kTcABytes);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (bf16) umma_issue_2sm<true>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
-              else umma_issue_2sm<false>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            }
-            umma_commit_2sm(empty0 + 8 * s);
-          }
-          umma_commit_2sm(tfull0 + 8 * acc);
-        }
-      }
-    }
-  } else {
-    const int lq = (warp & 3) * 32;
-    uint32_t tc = 0;
-    for (int pt = pair; pt < n_pair_tiles; pt += npairs) {
-      const int64_t i = static_cast<int64_t>(pt) * 2 * kTcBM + static_cast<int64_t>(rank) * kTcBM + lq + lane;
-      bool row_ok = i < a.n;
-      float xn = 0.f;
-      if (a.metric == EPS_METRIC_L2 && row_ok) xn = a.xnorm[a.row_start + i];
-      const int64_t row_abs = a.row_start + i;
-      if (a.D == nullptr && a.pass && row_ok) {
-        const int64_t pi = row_abs - a.pass_base;
-        row_ok = (a.pass[pi >> 5] >> (pi & 31)) & 1u;
-      }
-      for (int qt = 0; qt < a.n_q_tiles; ++qt, ++tc) {
-        const uint32_t acc = tc & 1, aph = (tc >> 1) & 1;
-        mbar_wait(tfull0 + 8 * acc, aph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int c = 0; c < kTcBN / 32; ++c) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lq) << 16) + acc * kTcBN + c * 32;
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int q0 = qt * kTcBN + c * 32;
-          if (a.D == nullptr) {
-            if (row_ok) {
-              const float m = a.metric == EPS_METRIC_L2 ? -2.0f : -1.0f;
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 ct = *reinterpret_cast<const float4*>(thr_s + q0 + 4 * j4);
-                const float t0 = fmaf(m, __uint_as_float(v[4 * j4 + 0]), xn), t1 = fmaf(m, __uint_as_float(v[4 * j4 + 1]), xn);
-                const float t2 = fmaf(m, __uint_as_float(v[4 * j4 + 2]), xn), t3 = fmaf(m, __uint_as_float(v[4 * j4 + 3]), xn);
-                if ((t0 < ct.x) | (t1 < ct.y) | (t2 < ct.z) | (t3 < ct.w)) {
-                  const float tt[4] = {t0, t1, t2, t3};
-                  const float cc[4] = {ct.x, ct.y, ct.z, ct.w};
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    if (tt[u] < cc[u]) {
-                      const int q = q0 + 4 * j4 + u;
-                      float d = tt[u];
-                      if (a.metric == EPS_METRIC_L2) d = fmaxf(d + qn_s[q], 0.f);
-                      else if (a.metric == EPS_METRIC_COSINE) d = 1.0f + d;
-                      const int slot = atomicAdd(&a.cand_cnt[q], 1);
-                      if (slot < a.cand_cap) a.cand[static_cast<int64_t>(q) * a.cand_cap + slot] = make_key(d, static_cast<uint32_t>(row_abs));
-                    }
-                  }
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int q = q0 + j;
-              if (row_ok && q < a.nq) {
-                const float dot = __uint_as_float(v[j]);
-                float d;
-                if (a.metric == EPS_METRIC_L2) d = fmaxf(xn + qn_s[q] - 2.0f * dot, 0.f);
-                else if (a.metric == EPS_METRIC_COSINE) d = 1.0f - dot;
-                else d = -dot;
-                a.D[static_cast<int64_t>(q) * a.ldd + i] = d;
-              }
-            }
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(tempty0 + 8 * acc);
-      }
-    }
-  }
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -665,7 +420,8 @@ __global__ void to_bf16_kernel(const float* __restrict__ in, int64_t n, unsigned
 }
 
 bool tc_dist_usable(const Index* ix, int64_t nq) {
-  if (getenv("EPS_NO_TC") || ix->coarse_mode == 0) return false;
+  static const bool env_off = getenv("EPS_NO_TC") != nullptr;  // read once
+  if (env_off || ix->coarse_mode == 0) return false;
   if (nq < 64 || nq > 1024) return false;            // per-query constants live in a 4 KB shared-memory table
   const int align = ix->coarse_mode == 2 ? 8 : 4;    // TMA: 16-byte row pitch
   if (ix->dim % align != 0 || ix->dim < 32) return false;
@@ -730,22 +486,15 @@ int tc_launch_distances(Index* ix, int64_t row_start, int64_t n, const float* d_
   }
   a.n_row_tiles = static_cast<int>((n + kTcBM - 1) / kTcBM);
   a.n_q_tiles = static_cast<int>((nq + kTcBN - 1) / kTcBN);
-  const char* dbg = getenv("EPS_TC_DEBUG");
-  a.debug = dbg ? atoi(dbg) : 0;
-  const char* epi = getenv("EPS_TC_EPI");
-  a.epi_pipelined = epi ? atoi(epi) : 0;
-  const bool two_cta = getenv("EPS_TC_2CTA") != nullptr && a.n_row_tiles >= 2 * ix->num_sms;
-  if (two_cta) {
-    // CTA pairs: B tensor map box = 128 queries (each CTA stages half of the 256-query block)
-    EPS_TRY(make_map(&tmB, b_base, nq, dim, kTcBN / 2, bf16));
-    EPS_CUDA(cudaFuncSetAttribute(tc_dist_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem));
-    const int grid2 = ix->num_sms & ~1;
-    tc_dist_kernel_2cta<<<grid2, kTcThreads, kTc2Smem, ix->stream>>>(tmA, tmB, a);
-  } else {
+  static const int env_epi = [] { const char* e = getenv("EPS_TC_EPI"); return e ? atoi(e) : 0; }();  // read once
+  a.epi_fast = env_epi == 2 ? 1 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
     EPS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-    const int grid = std::min(a.n_row_tiles, ix->num_sms);
-    tc_dist_kernel<<<grid, kTcThreads, kTcSmem, ix->stream>>>(tmA, tmB, a);
+    attr_set = true;
   }
+  const int grid = std::min(a.n_row_tiles, ix->num_sms);
+  tc_dist_kernel<<<grid, kTcThreads, kTcSmem, ix->stream>>>(tmA, tmB, a);
   EPS_CUDA(cudaGetLastError());
   ++*launches;
   return EPS_OK;
