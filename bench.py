@@ -79,6 +79,9 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--graph-file", default="", help="(reference-child) npz with the CSR to search")
     p.add_argument("--L", type=int, default=0, help="(reference arm) queue length; 0 = take it from the graph file / 512")
+    p.add_argument("--filter", default="", help="(reference-child) filter string for the reference's parser")
+    p.add_argument("--attr-mod", type=int, default=0, help="(reference-child) INT4 column ID = row %% this")
+    p.add_argument("--seed-shift", type=int, default=0, help="(reference-child) table seed = 42 + this (row shards)")
     return p.parse_args()
 
 
@@ -197,7 +200,7 @@ def reference_child(a):
     from oracle import oracle
     g = np.load(a.graph_file, allow_pickle=False)
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    X = gen_table(a.rows, a.dim, a.dist, 42, dev, a.centers)
+    X = gen_table(a.rows, a.dim, a.dist, 42 + a.seed_shift, dev, a.centers)
     if a.metric == "cosine":
         X /= X.norm(dim=1, keepdim=True)
     cores = os.cpu_count() or 1
@@ -226,6 +229,8 @@ def reference_child(a):
         r.vectors[r0:min(a.rows, r0 + step)] = X[r0:r0 + step].cpu().numpy()
     del X
     r.set_row_count(a.rows)
+    if a.attr_mod > 0:
+        r.set_attr_column("ID", (np.arange(a.rows) % a.attr_mod).astype(np.int32))
     if n_indexed > 0:
         r.set_graph(n_indexed, g["offsets"], g["nbrs"].astype(np.int64), int(g["nav"]))
         plans = [("i_defaults_16x4", min(16, max(1, cores // 4)), 4), ("ii_one_executor_per_core", cores, 1)]
@@ -237,18 +242,18 @@ def reference_child(a):
         vals = []
         for s in range(queries.shape[0]):
             t0 = time.perf_counter()
-            r.search_batch(queries[s], a.k)
+            r.search_batch(queries[s], a.k, a.filter)
             vals.append(queries.shape[1] / (time.perf_counter() - t0))
         out["modes"][name] = {"qps": vals, "n_exec": n_exec, "T": T}
     # sequential-order results (IntraQueryThreads = 1, one executor) of the first 32 queries of step 0: parity sample
     if n_indexed > 0:
         r.make_executors(1, 1, L)
-        ids, _, _ = r.search_batch(queries[0][:32], a.k)
+        ids, _, _ = r.search_batch(queries[0][:32], a.k, a.filter)
         out["ids_T1_step0"] = ids.tolist()
     print(json.dumps(out))
 
 
-def run_reference_child(a, graph, L, queries, timeout):
+def run_reference_child(a, graph, L, queries, timeout, filter_str="", attr_mod=0, seed_shift=0):
     """Spawn the child on `graph` = (n_indexed, offsets, nbrs, nav) or None; queries [steps, nq, dim] float32."""
     tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     path = os.path.join(tmpdir, "eps_bench_graph_%d.npz" % os.getpid())
@@ -259,7 +264,8 @@ def run_reference_child(a, graph, L, queries, timeout):
             np.savez(path, n_indexed=graph[0], offsets=graph[1], nbrs=np.asarray(graph[2], np.int32), nav=graph[3], L=L,
                      queries=queries)
         cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-child", "--graph-file", path, "--rows", str(a.rows),
-               "--dim", str(a.dim), "--dist", a.dist, "--centers", str(a.centers), "--metric", a.metric, "--k", str(a.k), "--L", str(L)]
+               "--dim", str(a.dim), "--dist", a.dist, "--centers", str(a.centers), "--metric", a.metric, "--k", str(a.k), "--L", str(L),
+               "--filter", filter_str, "--attr-mod", str(attr_mod), "--seed-shift", str(seed_shift)]
         env = dict(os.environ)
         for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "OMP_THREAD_LIMIT"):
             env.pop(k, None)  # torchrun sets OMP_NUM_THREADS=1 for its workers; the reference sizes its own teams
