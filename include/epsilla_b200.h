@@ -196,6 +196,29 @@ EPS_API int eps_merge_shards_device(int device, const int64_t* d_ids, const floa
                             int64_t k, int64_t* d_out_ids, float* d_out_dists);
 
 /* ---------------------------------------------------------------------------------------------
+ * Facets.  Replaces FacetExecutor::Aggregate (db/execution/aggregation.hpp:232-300), batched over nq result
+ * lists: one group-by expression (key_type = the ValueType ordinal of its root, query/expr/expr_types.hpp:67-74:
+ * 0 STRING -> the key is the row's dictionary code, 1 INT -> truncated like the reference's (int64_t) cast, 2 DOUBLE,
+ * 3 BOOL) and up to 8 aggregates, each an inner numeric expression with a type (NodeType ordinals 30 SUM, 31 MIN,
+ * 32 MAX, 33 COUNT — db_server.cpp:362-382 parses "SUM(expr)" into exactly this pair; COUNT's inner expression is
+ * "1").  Expressions are eps_filter_node arrays like the filters; "@distance" reads dists[i] (pass NULL when the
+ * caller has no distances: has_distance = false).  Output per query q: out_groups[q] groups in order of first
+ * appearance, keys out_keys[q*limit + g], values out_values[(q*limit + g)*n_aggs + a] (double, like the reference's
+ * aggregators).  HOST buffers in and out.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct eps_facet {
+  const eps_filter_node* key_nodes;
+  int64_t n_key_nodes;
+  int32_t key_type;
+  int32_t n_aggs;
+  const eps_filter_node* agg_nodes[8];
+  int64_t n_agg_nodes[8];
+  int32_t agg_types[8];
+} eps_facet;
+EPS_API int eps_facet_batch(eps_index* ix, const int64_t* ids, const double* dists, const int64_t* counts, int64_t nq,
+                            int64_t limit, const eps_facet* spec, double* out_keys, double* out_values, int64_t* out_groups);
+
+/* ---------------------------------------------------------------------------------------------
  * Row-sharded tables (one shard per GPU, one process or thread per GPU).  No reference counterpart: the reference
  * is single-segment (db/table_mvp.hpp:110); its own two-source merge of graph and tail results
  * (vec_search_executor.cpp:885-900) is the model.  The exchange (ONE ncclAllGather of nq*k*12 bytes per rank +

@@ -188,6 +188,11 @@ class Ref:
         L.ref_distance.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         L.ref_normalize.argtypes = [C.c_void_p, C.c_int64]
         L.ref_filter_eval.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_double]
+        L.ref_value_nodes.restype = C.c_int64
+        L.ref_value_nodes.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.ref_facet.restype = C.c_int64
+        L.ref_facet.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                C.c_char_p, C.c_int64]
         L.ref_filter_nodes.restype = C.c_int64
         L.ref_filter_nodes.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
         self.L = L
@@ -329,6 +334,28 @@ class Ref:
 
     def filter_eval(self, filter, row, dist=0.0):
         return self.L.ref_filter_eval(self.h, filter.encode(), row, dist)
+
+    def value_nodes(self, expr):
+        """Value expression (facet key / aggregate input) -> ([n,8] PODs, ValueType ordinal of the root)."""
+        out = np.zeros((64, 8), np.int64)
+        vt = C.c_int64(0)
+        n = self.L.ref_value_nodes(self.h, expr.encode(), _p(out), 64, C.byref(vt))
+        if n < 0:
+            raise ValueError("expression failed to parse: %r" % expr)
+        return out[:n].copy(), int(vt.value)
+
+    def facet(self, group_expr, agg_exprs, ids, dists=None):
+        """FacetExecutor::Aggregate + Project over one id list -> list of dicts (the reference's JSON array)."""
+        import json
+        ids = np.ascontiguousarray(ids, np.int64)
+        d = None if dists is None else np.ascontiguousarray(dists, np.float64)
+        arr = (C.c_char_p * len(agg_exprs))(*[e.encode() for e in agg_exprs])
+        buf = C.create_string_buffer(1 << 20)
+        n = self.L.ref_facet(self.h, group_expr.encode(), len(agg_exprs), arr, _p(ids), _p(d), ids.size, 0 if d is None else 1,
+                             buf, len(buf))
+        if n < 0:
+            raise ValueError("facet failed (%d)" % n)
+        return json.loads(buf.value.decode())
 
     def filter_nodes(self, filter):
         """Parsed node array as [n,8] int64 PODs (see oracle_port.c port_node)."""

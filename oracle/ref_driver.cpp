@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "db/ann_graph_segment.hpp"
+#include "db/execution/aggregation.hpp"
 #include "db/execution/vec_search_executor.hpp"
 #include "db/index/index.hpp"
 #include "db/table_segment_mvp.hpp"
@@ -295,6 +296,80 @@ int64_t ref_filter_nodes(void* h, const char* filter, int64_t* out, int64_t max_
     o[7] = off;
   }
   return n;
+}
+
+// Value expression (group-by key / aggregate input: Expr::ParseNodeFromStr(expr, nodes, map, false),
+// db_server.cpp:406,438) dumped as the same PODs as ref_filter_nodes; *root_value_type = ValueType of the root.
+int64_t ref_value_nodes(void* h, const char* expr, int64_t* out, int64_t max_nodes, int64_t* root_value_type) {
+  auto* c = static_cast<RefCtx*>(h);
+  std::vector<query::expr::ExprNodePtr> nodes;
+  auto st = query::expr::Expr::ParseNodeFromStr(expr, nodes, c->field_map, false);
+  if (!st.ok() || nodes.empty()) return -1;
+  int64_t n = static_cast<int64_t>(nodes.size());
+  if (n > max_nodes) return -2;
+  for (int64_t i = 0; i < n; ++i) {
+    auto& nd = nodes[i];
+    int64_t* o = out + i * 8;
+    o[0] = static_cast<int64_t>(nd->node_type);
+    o[1] = static_cast<int64_t>(nd->value_type);
+    o[2] = static_cast<int64_t>(nd->left);
+    o[3] = static_cast<int64_t>(nd->right);
+    o[4] = nd->int_value;
+    std::memcpy(&o[5], &nd->double_value, 8);
+    o[6] = nd->bool_value ? 1 : 0;
+    int64_t off = -1;
+    if (!nd->field_name.empty()) {
+      if (nd->field_name == "@distance") off = -2;
+      else {
+        auto it = c->seg->field_name_mem_offset_map_.find(nd->field_name);
+        off = it == c->seg->field_name_mem_offset_map_.end() ? -1 : static_cast<int64_t>(it->second);
+      }
+    }
+    o[7] = off;
+  }
+  *root_value_type = static_cast<int64_t>(nodes[n - 1]->value_type);
+  return n;
+}
+
+// FacetExecutor (db/execution/aggregation.hpp:124-413) over one id list, set up the way db_server.cpp:384-456 does:
+// one group-by expression ("" = global group, expression "1"), aggregates "SUM(expr)" / "MIN(..)" / "MAX(..)" /
+// "COUNT(..)".  Writes the Project() JSON array into out (NUL-terminated); returns its length, -1 on a parse error.
+int64_t ref_facet(void* h, const char* group_expr, int n_aggs, const char* const* agg_exprs, const int64_t* ids,
+                  const double* dists, int64_t n, int has_distance, char* out, int64_t cap) {
+  auto* c = static_cast<RefCtx*>(h);
+  const bool global = group_expr == nullptr || group_expr[0] == 0;
+  std::vector<std::string> group_exprs{global ? std::string("1") : std::string(group_expr)};
+  std::vector<std::vector<query::expr::ExprNodePtr>> group_nodes(1);
+  if (!query::expr::Expr::ParseNodeFromStr(group_exprs[0], group_nodes[0], c->field_map, false).ok()) return -1;
+  std::vector<std::string> aggs;
+  std::vector<query::expr::NodeType> types;
+  std::vector<std::vector<query::expr::ExprNodePtr>> agg_nodes;
+  for (int i = 0; i < n_aggs; ++i) {
+    std::string e = agg_exprs[i], up = e, inner;
+    for (auto& ch : up) ch = static_cast<char>(std::toupper(static_cast<unsigned char>(ch)));
+    query::expr::NodeType t;
+    if (up.rfind("SUM(", 0) == 0 && up.back() == ')') { t = query::expr::NodeType::SumAggregation; inner = e.substr(4, e.size() - 5); }
+    else if (up.rfind("MAX(", 0) == 0 && up.back() == ')') { t = query::expr::NodeType::MaxAggregation; inner = e.substr(4, e.size() - 5); }
+    else if (up.rfind("MIN(", 0) == 0 && up.back() == ')') { t = query::expr::NodeType::MinAggregation; inner = e.substr(4, e.size() - 5); }
+    else if (up.rfind("COUNT(", 0) == 0 && up.back() == ')') { t = query::expr::NodeType::CountAggregation; inner = "1"; }
+    else return -1;
+    std::vector<query::expr::ExprNodePtr> nodes;
+    if (!query::expr::Expr::ParseNodeFromStr(inner, nodes, c->field_map, false).ok()) return -1;
+    aggs.push_back(e);
+    types.push_back(t);
+    agg_nodes.push_back(nodes);
+  }
+  execution::FacetExecutor fx(global, group_exprs, group_nodes, types, aggs, agg_nodes);
+  std::vector<int64_t> idv(ids, ids + n);
+  std::vector<double> dv;
+  if (has_distance) dv.assign(dists, dists + n);
+  fx.Aggregate(c->seg.get(), n, idv, has_distance != 0, dv);
+  vectordb::Json result;
+  fx.Project(result);
+  std::string text = result.DumpToString();
+  if (static_cast<int64_t>(text.size()) + 1 > cap) return -2;
+  std::memcpy(out, text.c_str(), text.size() + 1);
+  return static_cast<int64_t>(text.size());
 }
 
 }  // extern "C"

@@ -572,3 +572,56 @@ def test_string_codes_filter_through_c_abi(vdb):
     with pytest.raises(Exception):   # a column that is not mirrored for every row must be refused, not read out of bounds
         ix.search(Q, k, filter_nodes=np.array([[S_ATTR, 0, -1, -1, 0, 0, 0, 1], [S_CONST, 0, -1, -1, 0, 0, 0, -1], [EQ, 3, 0, 1, 0, 0, 0, -1]], np.int64))
     ix.close()
+
+
+def test_facets_match_reference(vdb, have_ref):
+    """f4: FacetExecutor::Aggregate on the device (eps_facet_batch) against the reference's own FacetExecutor on the
+    same result lists: int / double / bool / string keys, SUM / COUNT / MIN / MAX, '@distance' inside an aggregate."""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libepsilla_ref.so did not travel")
+    from oracle.oracle import Ref
+    n, d, nq, k = 4000, 16, 12, 64
+    X, Q = gen(n, d, 111), gen(nq, d, 112)
+    rng = np.random.default_rng(113)
+    cols = [("ID", "int4"), ("w", "double"), ("flag", "bool"), ("name", "string")]
+    r = Ref("l2", d, n, cols)
+    r.set_rows(X)
+    idv, wv, fv = np.arange(n), rng.random(n), rng.integers(0, 2, n)
+    names = ["n%d" % v for v in rng.integers(0, 9, n)]
+    for nm, v in (("ID", idv), ("w", wv), ("flag", fv)):
+        r.set_attr_column(nm, v)
+    r.set_string_column("name", names)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.set_attrs(r.attrs[: n * r.stride].copy(), r.stride, n)
+    dictionary = {s: i for i, s in enumerate(sorted(set(names)))}
+    back = {i: s for s, i in dictionary.items()}
+    ix.set_string_codes(r.attr_offset("name"), 0, np.array([dictionary[s] for s in names], np.int32))
+    ix.config(500, 500, force_brute=True)
+    ids, ds, cnt, _ = ix.search(Q, k)
+    AGG = {"SUM": 30, "MIN": 31, "MAX": 32, "COUNT": 33}
+    cases = [("ID % 7", ["SUM(w)", "COUNT(*)", "MIN(ID)", "MAX(w * 2 + @distance)"]), ("name", ["COUNT(*)", "SUM(ID)"]),
+             ("flag", ["COUNT(*)", "MAX(@distance)"]), ("w * 2", ["COUNT(*)"]), ("", ["COUNT(*)", "SUM(w)", "MIN(@distance)"])]
+    for group, aggs in cases:
+        knodes, ktype = r.value_nodes(group if group else "1")
+        alist = []
+        for a in aggs:
+            inner = "1" if a.upper().startswith("COUNT(") else a[a.index("(") + 1:-1]
+            alist.append((AGG[a[:a.index("(")].upper()], r.value_nodes(inner)[0]))
+        got = ix.facet(ids, cnt, knodes, ktype, alist, dists=ds)
+        for q in range(nq):
+            want = r.facet(group, aggs, ids[q, :cnt[q]], ds[q, :cnt[q]])
+            assert len(got[q]) == len(want), (group, q)
+            wmap = {}
+            for obj in want:
+                key = obj.get(group, 1) if group else 1
+                wmap[key] = [obj[a] for a in aggs]
+            for key, vals in got[q]:
+                kk = back[int(key)] if ktype == 0 else (bool(key) if ktype == 3 else (int(key) if ktype == 1 else key))
+                if ktype == 2:
+                    kk = min(wmap, key=lambda x: abs(x - key))
+                    assert abs(kk - key) <= 1e-12 * max(1.0, abs(key))
+                ref_vals = wmap[kk]
+                for v, w in zip(vals, ref_vals):
+                    assert abs(v - w) <= 1e-9 * max(1.0, abs(w)) or (isinstance(w, int) and int(v) == w), (group, q, kk, vals, ref_vals)
+    ix.close()

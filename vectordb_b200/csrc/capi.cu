@@ -148,6 +148,36 @@ static void free_graph(Index* ix) {
   ix->n_edges = 0;
 }
 
+// Every attribute read of a lowered program must stay inside the mirrored row-major attribute table; string columns
+// are bound to their device code arrays.
+int bind_program_columns(Index* ix, FilterProg* prog) {
+  for (int i = 0; i < prog->n; ++i) {
+    const FNode& nd = prog->nodes[i];
+    int width = 0;
+    switch (nd.type) {
+      case NT_Int1Attr: case NT_BoolAttr: width = 1; break;
+      case NT_Int2Attr: width = 2; break;
+      case NT_Int4Attr: case NT_FloatAttr: width = 4; break;
+      case NT_Int8Attr: case NT_DoubleAttr: width = 8; break;
+      default: break;
+    }
+    if (nd.type == NT_StringAttr) {
+      const StrCol& sc = ix->str_cols[nd.field_offset];
+      if (!sc.d_codes || sc.rows < ix->n_rows)
+        return fail(EPS_ERR_INVALID_ARGUMENT, "expression reads a string column whose dictionary codes are not mirrored for every row");
+      prog->str_col[nd.field_offset] = sc.d_codes;
+      continue;
+    }
+    if (width == 0 || nd.field_offset < 0) continue;  // constants, operators, the @distance pseudo-field
+    if (!ix->d_attrs) return fail(EPS_ERR_INVALID_ARGUMENT, "expression reads attributes but eps_index_set_attrs was not called");
+    if (static_cast<int64_t>(nd.field_offset) + width > ix->attr_stride)
+      return fail(EPS_ERR_INVALID_ARGUMENT, "field offset lies outside the attribute row");
+    if (ix->attr_rows < ix->n_rows)
+      return fail(EPS_ERR_INVALID_ARGUMENT, "attribute mirror has fewer rows than the vector mirror (call eps_index_set_attrs)");
+  }
+  return EPS_OK;
+}
+
 static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t limit, const eps_filter_node* filter,
                          int64_t n_filter, int64_t* d_ids, float* d_dists, int64_t* d_counts, eps_stats* stats) {
   if (nq <= 0) return EPS_OK;
@@ -156,31 +186,7 @@ static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t 
   EPS_TRY(lower_filter(filter, n_filter, &h_prog));
   const FilterProg* d_prog = nullptr;
   if (h_prog.n > 0) {
-    // every attribute read must stay inside the mirrored row-major attribute table
-    for (int i = 0; i < h_prog.n; ++i) {
-      const FNode& nd = h_prog.nodes[i];
-      int width = 0;
-      switch (nd.type) {
-        case NT_Int1Attr: case NT_BoolAttr: width = 1; break;
-        case NT_Int2Attr: width = 2; break;
-        case NT_Int4Attr: case NT_FloatAttr: width = 4; break;
-        case NT_Int8Attr: case NT_DoubleAttr: width = 8; break;
-        default: break;
-      }
-      if (nd.type == NT_StringAttr) {
-        const eps::StrCol& sc = ix->str_cols[nd.field_offset];
-        if (!sc.d_codes || sc.rows < ix->n_rows)
-          return fail(EPS_ERR_INVALID_ARGUMENT, "filter reads a string column whose dictionary codes are not mirrored for every row");
-        h_prog.str_col[nd.field_offset] = sc.d_codes;
-        continue;
-      }
-      if (width == 0 || nd.field_offset < 0) continue;  // constants, operators, the @distance pseudo-field
-      if (!ix->d_attrs) return fail(EPS_ERR_INVALID_ARGUMENT, "filter reads attributes but eps_index_set_attrs was not called");
-      if (static_cast<int64_t>(nd.field_offset) + width > ix->attr_stride)
-        return fail(EPS_ERR_INVALID_ARGUMENT, "filter field offset lies outside the attribute row");
-      if (ix->attr_rows < ix->n_rows)
-        return fail(EPS_ERR_INVALID_ARGUMENT, "attribute mirror has fewer rows than the vector mirror (call eps_index_set_attrs)");
-    }
+    EPS_TRY(bind_program_columns(ix, &h_prog));
     EPS_TRY(ix->s_filter.reserve(sizeof(FilterProg)));
     EPS_CUDA(cudaMemcpyAsync(ix->s_filter.p, &h_prog, sizeof(FilterProg), cudaMemcpyHostToDevice, ix->stream));
     // h_prog lives on this stack frame until the sync at the end of the caller's timing region; the copy

@@ -51,10 +51,10 @@ struct FilterProg {
 // Host: validate + lower eps_filter_node[] to FilterProg.  Returns EPS_* code.
 int lower_filter(const eps_filter_node* nodes, int64_t n, FilterProg* out);
 
-__device__ __forceinline__ bool filter_eval(const FilterProg& p, const char* __restrict__ attrs, int64_t stride,
-                                            int64_t row, float distance) {
-  if (p.n == 0) return true;
-  const double dist = p.root_uses_dist ? static_cast<double>(distance) : 0.0;
+// One forward pass over the program; the root's numeric and logical values come back through *num_out / *bool_out.
+// `dist` is what "@distance" reads.
+__device__ __forceinline__ void prog_run(const FilterProg& p, const char* __restrict__ attrs, int64_t stride, int64_t row,
+                                         double dist, double* num_out, bool* bool_out) {
   double num[kMaxFilterNodes];
   bool bl[kMaxFilterNodes];
   const char* base = attrs + row * stride;
@@ -104,7 +104,27 @@ __device__ __forceinline__ bool filter_eval(const FilterProg& p, const char* __r
     num[i] = v;
     bl[i] = b;
   }
-  return bl[p.n - 1];
+  *num_out = num[p.n - 1];
+  *bool_out = bl[p.n - 1];
+}
+
+// LogicalEvaluate(root, row, distance) (:170-258): the distance is visible only when the root is a numeric comparison.
+__device__ __forceinline__ bool filter_eval(const FilterProg& p, const char* __restrict__ attrs, int64_t stride,
+                                            int64_t row, float distance) {
+  if (p.n == 0) return true;
+  double nv;
+  bool bv;
+  prog_run(p, attrs, stride, row, p.root_uses_dist ? static_cast<double>(distance) : 0.0, &nv, &bv);
+  return bv;
+}
+
+// NumEvaluate(root, row, distance) (:127-164): the distance reaches "@distance" at any depth of the arithmetic.
+__device__ __forceinline__ double value_eval(const FilterProg& p, const char* __restrict__ attrs, int64_t stride, int64_t row,
+                                             double distance) {
+  double nv = 0.0;
+  bool bv = false;
+  if (p.n > 0) prog_run(p, attrs, stride, row, distance, &nv, &bv);
+  return nv;
 }
 
 }  // namespace eps

@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-from .lib import BuildParams, FilterNode, StatsStruct, check, load_library
+from .lib import BuildParams, FacetSpec, FilterNode, StatsStruct, check, load_library
 
 METRICS = {"l2": 1, "euclidean": 1, "cosine": 2, "cos": 2, "ip": 3, "dot": 3, "dot_product": 3}
 
@@ -145,6 +145,29 @@ class Index:
                                              C.c_void_p(d_ids_ptr), C.c_void_p(d_dists_ptr), C.c_void_p(d_counts_ptr),
                                              C.byref(st) if want_stats else None, int(bool(sync))))
         return Stats.from_struct(st)
+
+    def facet(self, ids, counts, key_nodes, key_type, aggs, dists=None):
+        """FacetExecutor::Aggregate over result lists (eps_facet_batch).  key_nodes: [n,8] PODs of the group-by
+        expression; key_type: 0 string (dictionary code), 1 int, 2 double, 3 bool; aggs: [(agg_type, nodes)] with
+        agg_type 30 SUM / 31 MIN / 32 MAX / 33 COUNT.  Returns per query a list of (key, [values])."""
+        ids = np.ascontiguousarray(ids, np.int64)
+        nq, limit = ids.shape
+        counts = np.ascontiguousarray(counts, np.int64)
+        d = None if dists is None else np.ascontiguousarray(dists, np.float64)
+        spec = FacetSpec()
+        keep = []
+        karr, kn = filter_nodes_array(key_nodes)
+        keep.append(karr)
+        spec.key_nodes, spec.n_key_nodes, spec.key_type, spec.n_aggs = C.cast(karr, C.c_void_p), kn, int(key_type), len(aggs)
+        for i, (t, nodes) in enumerate(aggs):
+            arr, n = filter_nodes_array(nodes)
+            keep.append(arr)
+            spec.agg_nodes[i], spec.n_agg_nodes[i], spec.agg_types[i] = C.cast(arr, C.c_void_p), n, int(t)
+        ok = np.empty((nq, limit), np.float64)
+        ov = np.empty((nq, limit, len(aggs)), np.float64)
+        og = np.empty(nq, np.int64)
+        check(self.L.eps_facet_batch(self.h, _p(ids), _p(d), _p(counts), nq, limit, C.byref(spec), _p(ok), _p(ov), _p(og)))
+        return [[(ok[q, g], ov[q, g].tolist()) for g in range(og[q])] for q in range(nq)]
 
     @property
     def stream(self):
