@@ -521,6 +521,8 @@ def main():
         r = {"mode": m[0], "L": m[1], "coarse": m[2], key_rec: rec, "qps_probe": qps}
         if stats[0] is not None:
             r["n_dist_per_query"] = float(np.mean([s["n_dist"] for s in stats])) / a.batch
+            if m[0] == "brute":
+                r["queries_redone_by_guard_per_step"] = float(np.mean([s["n_redone"] for s in stats]))
         report.append(r)
         return r
 

@@ -73,6 +73,7 @@ typedef struct eps_stats {
   double kernel_ms;    /* device time of the dominant kernel(s) of this call (CUDA events) */
   double total_ms;     /* device time of the whole call incl. copies (CUDA events) */
   uint64_t kernel_launches;
+  uint64_t n_redone;   /* exact scan: queries the coarse-pass guard sent back (fp32 scan or a larger candidate list) */
 } eps_stats;
 
 /* Graph-build parameters.  Defaults (pass NULL) follow NSGConfig(45, 50, 300, 100) and the
@@ -165,10 +166,14 @@ EPS_API int eps_index_set_graph_tuning(eps_index* ix, int ring_slots, int ctas_p
 
 /* Precision of the COARSE pass of large-batch exact scans (nq >= 64): 0 = none (fp32 SIMT tiles only),
  * 1 = tcgen05 kind::tf32 on the fp32 rows (default), 2 = tcgen05 kind::f16 on a bf16 mirror of the table
- * (+50 % HBM).  Whatever the mode, the k + max(32, k) best coarse candidates of every query are re-evaluated
- * with the exact fp32 direct form, so returned distances are fp32-exact and ids differ from mode 0 only if a
- * true top-k row fell outside the coarse candidate list. */
+ * (+50 % HBM).  Whatever the mode, the k' = k + max(118, k) best coarse candidates of every query are re-evaluated
+ * with the exact fp32 direct form, so returned distances are fp32-exact, and a GUARD checks that no row outside
+ * the candidate list can belong to the answer: with T = the k'-th best coarse distance, e_k = the exact k-th best
+ * and E = the largest |coarse - exact| over the batch's own k' x nq re-scored rows, a query is safe when
+ * e_k + 2 E <= T; unsafe queries are redone on the fp32 path (or, when many are unsafe, the batch is redone with a
+ * 4x larger k' that the index remembers).  eps_stats.n_redone counts them.  The guard is on by default. */
 EPS_API int eps_index_set_coarse(eps_index* ix, int mode);
+EPS_API int eps_index_set_coarse_guard(eps_index* ix, int on);
 
 /* ---------------------------------------------------------------------------------------------
  * Search.  Replaces VecSearchExecutor::Search (db/execution/vec_search_executor.cpp:833-935),

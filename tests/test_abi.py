@@ -32,7 +32,7 @@ def test_header_symbols_exported():
 def test_struct_layouts_match_header():
     from vectordb_b200.lib import BuildParams, FilterNode, StatsStruct
     assert C.sizeof(FilterNode) == 64
-    assert C.sizeof(StatsStruct) == 64
+    assert C.sizeof(StatsStruct) == 72
     assert C.sizeof(BuildParams) == 48
 
 
@@ -72,7 +72,7 @@ def test_header_is_plain_c(tmp_path):
         "int main(void) {\n"
         "  eps_filter_node n; eps_stats s; eps_build_params b; eps_index* ix = NULL;\n"
         "  (void)n; (void)s; (void)b;\n"
-        "  if (sizeof(eps_filter_node) != 64 || sizeof(eps_stats) != 64) return 2;\n"
+        "  if (sizeof(eps_filter_node) != 64 || sizeof(eps_stats) != 72) return 2;\n"
         "  /* no device in this container: creation must fail loudly, never fall back */\n"
         "  return eps_index_create(&ix, EPS_METRIC_L2, 8, NULL, 0, 0) == EPS_OK && eps_device_count() == 0 ? 3 : 0;\n"
         "}\n")

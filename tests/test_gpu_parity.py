@@ -625,3 +625,40 @@ def test_facets_match_reference(vdb, have_ref):
                 for v, w in zip(vals, ref_vals):
                     assert abs(v - w) <= 1e-9 * max(1.0, abs(w)) or (isinstance(w, int) and int(v) == w), (group, q, kk, vals, ref_vals)
     ix.close()
+
+
+def test_exact_scan_guard_catches_a_coarse_pass_that_cannot_rank(vdb):
+    """Weak point 1 of round 1: exactness of the tensor-core scan must be enforced, not hoped for.  On a table whose
+    rows differ by far less than a bf16 rounding step the coarse pass cannot rank anything; the guard (exact k-th best
+    + 2 x the batch's largest observed coarse error must not exceed the coarse k'-th threshold) has to notice and the
+    answer must still be the fp32 scan's.  On ordinary data the guard stays silent."""
+    n, d, nq, k = 100000, 64, 128, 10
+    rng = np.random.default_rng(7)
+    base = rng.random(d, dtype=np.float32)
+    X = (base[None, :] + 1e-3 * rng.standard_normal((n, d))).astype(np.float32)
+    Q = (base[None, :] + 1e-3 * rng.standard_normal((nq, d))).astype(np.float32)
+    ix = vdb.Index("l2", d, host_vectors=X)
+    ix.sync_rows(n)
+    ix.config(500, 500, force_brute=True)
+    ix.set_coarse("fp32")
+    want, wd, _, _ = ix.search(Q, k)
+    for mode in ("bf16", "tf32"):
+        ix.set_coarse(mode)
+        got, gd, _, st = ix.search(Q, k)
+        assert st["n_redone"] > 0, mode
+        assert np.allclose(gd, wd, rtol=1e-5) and (got == want).mean() > 0.999, mode
+    ix.set_coarse_guard(False)                    # the unguarded pass really is wrong here: the test has teeth
+    ix.set_coarse("bf16")
+    raw, _, _, st0 = ix.search(Q, k)
+    assert st0["n_redone"] == 0 and (raw == want).mean() < 0.9
+    ix.close()
+    X2, Q2 = gen(200000, d, 8), gen(nq, d, 9)
+    ix = vdb.Index("l2", d, host_vectors=X2)
+    ix.sync_rows(200000)
+    ix.config(500, 500, force_brute=True)
+    ix.set_coarse("fp32")
+    want, _, _, _ = ix.search(Q2, k)
+    ix.set_coarse("bf16")
+    got, _, _, st = ix.search(Q2, k)
+    assert st["n_redone"] == 0 and (got == want).mean() > 0.999
+    ix.close()

@@ -376,7 +376,7 @@ __global__ void fill_keys_kernel(unsigned long long* p, int64_t n, unsigned long
 __global__ void __launch_bounds__(128) rescore_kernel(const float* __restrict__ vectors, int dim, int metric, int vec4,
                                                      const float* __restrict__ queries,
                                                      const unsigned long long* __restrict__ coarse, int kc, int kcp, int k,
-                                                     unsigned long long* __restrict__ out) {
+                                                     unsigned long long* __restrict__ out, unsigned* __restrict__ err_max_bits) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(rs_smem);  // [kcp]
   float* qv = reinterpret_cast<float*>(keys + kcp);
@@ -391,12 +391,47 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float* __restrict__ 
       const uint32_t id = key_id(ck);
       const float d = warp_distance(metric, vec4 != 0, vectors + static_cast<int64_t>(id) * dim, qv, dim, lane);
       key = make_key(d, id);
+      // calibration sample of the coarse pass: |coarse - exact| of a re-scored row (non-negative floats order as uints)
+      if (lane == 0 && err_max_bits) atomicMax(err_max_bits, __float_as_uint(fabsf(key_dist(ck) - d)));
     }
     if (lane == 0) keys[c] = key;
   }
   __syncthreads();
   block_bitonic_sort(keys, kcp);
   for (int i = tid; i < k; i += blockDim.x) out[static_cast<int64_t>(q) * k + i] = keys[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exactness guard of the coarse pass.  A row outside the coarse top-k' has coarse distance >= T (the k'-th best
+// coarse value); it can only belong to the exact top-k if its coarse error exceeds T - e_k (e_k = exact k-th best
+// after the re-score).  The batch's own re-scored rows (k' x nq samples of |coarse - exact|, whatever the operand
+// format or rounding mode did) calibrate the error: a query is SAFE when e_k + 2 * max|coarse - exact| <= T, or when
+// fewer than k' rows exist at all.  Unsafe queries are redone (exact fp32 scan, or the whole batch with a larger k').
+// ------------------------------------------------------------------------------------------------
+__global__ void verify_exact_kernel(const unsigned long long* __restrict__ final_keys, int k_final, const float* __restrict__ thr,
+                                    const unsigned* __restrict__ err_max_bits, int nq, int* __restrict__ flags,
+                                    int* __restrict__ n_flagged) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const unsigned long long kth = final_keys[static_cast<int64_t>(q) * k_final + (k_final - 1)];
+  const float T = thr[q];
+  const float eps = 2.0f * __uint_as_float(*err_max_bits);
+  const bool unsafe = (kth & kKeyMask) != kKeyInf && !isinf(T) && !(key_dist(kth) + eps <= T);
+  flags[q] = unsafe ? 1 : 0;
+  if (unsafe) atomicAdd(n_flagged, 1);
+}
+
+__global__ void gather_queries_kernel(const float* __restrict__ queries, const int* __restrict__ idx, int n, int dim,
+                                      float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(n) * dim) return;
+  out[i] = queries[static_cast<int64_t>(idx[i / dim]) * dim + (i % dim)];
+}
+__global__ void scatter_keys_kernel(const unsigned long long* __restrict__ in, const int* __restrict__ idx, int n, int k,
+                                    unsigned long long* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(n) * k) return;
+  out[static_cast<int64_t>(idx[i / k]) * k + (i % k)] = in[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -447,6 +482,8 @@ int launch_distances(Index* ix, const float* A_base, int64_t row_start, int64_t 
 static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_start, int64_t row_end, int64_t k,
                      const FilterProg* d_prog, const FilterProg* h_prog, bool prefilter, int64_t self_base,
                      unsigned long long* d_topk, eps_stats* stats, bool allow_tc = true) {
+  // never-shrinking scratch owned by the index would be overwritten by the nested fp32 redo of unsafe queries
+  // (that redo never takes the tensor-core branch, so it uses none of the coarse-pass buffers)
   if (k < 1 || k > 8192) return fail(EPS_ERR_UNSUPPORTED, "brute-force top-k supports 1 <= k <= 8192");
   uint64_t launches = 0;
   const int64_t n = row_end - row_start;
@@ -457,7 +494,8 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
   unsigned long long* d_final = d_topk;
   const bool use_tc = allow_tc && n >= 4096 && self_base < 0 && !dyn_filter && tc_dist_usable(ix, nq) && d_queries != ix->d_vectors;
   if (use_tc) {
-    k = std::min<int64_t>(8192, k_final + std::max<int64_t>(32, k_final));
+    // k' coarse candidates per query: k + max(118, k) (128 for top-10), times the boost the guard has learnt
+    k = std::min<int64_t>(8192, (k_final + std::max<int64_t>(118, k_final)) * std::max(1, ix->coarse_boost));
     EPS_TRY(ix->s_coarse.reserve(static_cast<size_t>(nq) * k * 8));
     d_topk = ix->s_coarse.as<unsigned long long>();
   }
@@ -514,14 +552,14 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     EPS_CUDA(cudaFuncSetAttribute(bf_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
     EPS_CUDA(cudaFuncSetAttribute(bf_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
   }
-  const int cand_cap = 4096;
+  const int cand_cap = static_cast<int>(std::max<int64_t>(4096, 16 * k));  // fused launches grow 8x: ~8 k' survivors each
   int* d_overflow = nullptr;
   if (use_tc) {
     EPS_TRY(ix->s_thr.reserve(static_cast<size_t>(nq) * 4));
     EPS_TRY(ix->s_cand.reserve(static_cast<size_t>(nq) * cand_cap * 8));
-    EPS_TRY(ix->s_cand_cnt.reserve(static_cast<size_t>(nq + 1) * 4));
-    d_overflow = ix->s_cand_cnt.as<int>() + nq;
-    EPS_CUDA(cudaMemsetAsync(d_overflow, 0, 4, ix->stream));
+    EPS_TRY(ix->s_cand_cnt.reserve(static_cast<size_t>(nq + 4) * 4));
+    d_overflow = ix->s_cand_cnt.as<int>() + nq;  // [overflow, n_flagged, err_max bits]
+    EPS_CUDA(cudaMemsetAsync(d_overflow, 0, 12, ix->stream));
   }
   for (int64_t c0 = 0; c0 < n;) {
     // Chunk 0 (and every chunk of the SIMT path) materialises the [nq x chunk] distance tile and selects from
@@ -559,13 +597,66 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     c0 += cn;
   }
   if (use_tc) {
-    // candidate buffers are sized for the expected k'/c survivors per query; an adversarial row order can
-    // overflow them — detected here, and the call is redone on the fp32 path (never silently truncated)
-    int h_overflow = 0;
-    EPS_CUDA(cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, ix->stream));
+    const int kc = static_cast<int>(k), kcp = next_pow2(kc);
+    const size_t rs_smem = static_cast<size_t>(kcp) * 8 + static_cast<size_t>((ix->dim + 3) & ~3ll) * 4;
+    if (rs_smem > 48 * 1024)
+      EPS_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem)));
+    unsigned* d_err = reinterpret_cast<unsigned*>(d_overflow + 2);
+    rescore_kernel<<<static_cast<unsigned>(nq), 128, rs_smem, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), ix->metric,
+                                                                          ix->vec4 ? 1 : 0, d_queries, d_topk, kc, kcp,
+                                                                          static_cast<int>(k_final), d_final, d_err);
+    EPS_CUDA(cudaGetLastError());
+    ++launches;
+    std::vector<int> h_flags;
+    int h_state[2] = {0, 0};  // overflow, n_flagged
+    const bool guard = ix->coarse_guard != 0;
+    if (guard) {
+      EPS_TRY(ix->s_flags.reserve(static_cast<size_t>(nq) * 4));
+      verify_exact_kernel<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, ix->stream>>>(
+          d_final, static_cast<int>(k_final), ix->s_thr.as<float>(), d_err, static_cast<int>(nq), ix->s_flags.as<int>(), d_overflow + 1);
+      EPS_CUDA(cudaGetLastError());
+      ++launches;
+      h_flags.resize(static_cast<size_t>(nq));
+      EPS_CUDA(cudaMemcpyAsync(h_flags.data(), ix->s_flags.p, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, ix->stream));
+    }
+    // ONE host round trip per tensor-core scan: candidate-buffer overflow (adversarial row order: the buffers are
+    // sized for the expected survivors) and the guard's verdict
+    EPS_CUDA(cudaMemcpyAsync(h_state, d_overflow, 8, cudaMemcpyDeviceToHost, ix->stream));
     EPS_CUDA(cudaStreamSynchronize(ix->stream));
-    if (h_overflow)
+    if (stats) stats->kernel_launches += launches;
+    if (h_state[0])  // never silently truncated: the call is redone on the fp32 path
       return topk_impl(ix, d_queries, nq, row_start, row_end, k_final, d_prog, h_prog, prefilter, self_base, d_final, stats, false);
+    if (guard && h_state[1] > 0) {
+      const int64_t n_bad = h_state[1];
+      if (n_bad > std::max<int64_t>(8, nq / 32) && k < 4096) {
+        // too many unsafe queries for this table's distance spread: remember a 4x larger k' and redo the batch
+        ix->coarse_boost = std::min(64, std::max(1, ix->coarse_boost) * 4);
+        if (stats) stats->n_redone += static_cast<uint64_t>(nq);
+        return topk_impl(ix, d_queries, nq, row_start, row_end, k_final, d_prog, h_prog, prefilter, self_base, d_final, stats, true);
+      }
+      // a few unsafe queries: exact fp32 scan for those only
+      std::vector<int> idx;
+      for (int64_t q = 0; q < nq; ++q) if (h_flags[q]) idx.push_back(static_cast<int>(q));
+      DevBuf d_idx, d_q, d_res;
+      EPS_TRY(d_idx.reserve(idx.size() * 4));
+      EPS_TRY(d_q.reserve(idx.size() * ix->dim * 4));
+      EPS_TRY(d_res.reserve(idx.size() * k_final * 8));
+      EPS_CUDA(cudaMemcpyAsync(d_idx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+      const int64_t tot = static_cast<int64_t>(idx.size()) * ix->dim;
+      gather_queries_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(d_queries, d_idx.as<int>(), static_cast<int>(idx.size()),
+                                                                                             static_cast<int>(ix->dim), d_q.as<float>());
+      EPS_CUDA(cudaGetLastError());
+      EPS_TRY(topk_impl(ix, d_q.as<float>(), static_cast<int64_t>(idx.size()), row_start, row_end, k_final, d_prog, h_prog, prefilter, -1,
+                        d_res.as<unsigned long long>(), nullptr, false));
+      const int64_t tk = static_cast<int64_t>(idx.size()) * k_final;
+      scatter_keys_kernel<<<static_cast<unsigned>((tk + 255) / 256), 256, 0, ix->stream>>>(d_res.as<unsigned long long>(), d_idx.as<int>(),
+                                                                                           static_cast<int>(idx.size()), static_cast<int>(k_final), d_final);
+      EPS_CUDA(cudaGetLastError());
+      EPS_CUDA(cudaStreamSynchronize(ix->stream));  // the temporaries die with this frame
+      if (stats) { stats->n_redone += static_cast<uint64_t>(idx.size()); stats->kernel_launches += 2; }
+    }
+    if (stats) stats->n_dist += static_cast<uint64_t>(nq) * static_cast<uint64_t>(n);
+    return EPS_OK;
   }
   if (nsplit > 1) {
     SelectArgs a;
@@ -575,17 +666,6 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     bf_select_kernel<true><<<dim3(static_cast<unsigned>(nq), 1), kSelThreads, sel_smem, ix->stream>>>(a);
     ++launches;
     EPS_CUDA(cudaGetLastError());
-  }
-  if (use_tc) {
-    const int kc = static_cast<int>(k), kcp = next_pow2(kc);
-    const size_t rs_smem = static_cast<size_t>(kcp) * 8 + static_cast<size_t>((ix->dim + 3) & ~3ll) * 4;
-    if (rs_smem > 48 * 1024)
-      EPS_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem)));
-    rescore_kernel<<<static_cast<unsigned>(nq), 128, rs_smem, ix->stream>>>(ix->d_vectors, static_cast<int>(ix->dim), ix->metric,
-                                                                          ix->vec4 ? 1 : 0, d_queries, d_topk, kc, kcp,
-                                                                          static_cast<int>(k_final), d_final);
-    EPS_CUDA(cudaGetLastError());
-    ++launches;
   }
   if (stats) {
     stats->n_dist += static_cast<uint64_t>(nq) * static_cast<uint64_t>(n);

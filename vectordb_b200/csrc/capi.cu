@@ -242,6 +242,7 @@ static int search_device(Index* ix, const float* d_queries, int64_t nq, int64_t 
     stats->n_edges += local.n_edges;
     stats->n_queries += static_cast<uint64_t>(nq);
     stats->kernel_launches += local.kernel_launches;
+    stats->n_redone += local.n_redone;
   }
   return EPS_OK;
 }
@@ -305,7 +306,7 @@ void eps_index_destroy(eps_index* h) {
   for (auto& sc : ix->str_cols) if (sc.d_codes) cudaFree(sc.d_codes);
   eps::DevBuf* bufs[] = {&ix->s_queries, &ix->s_dist, &ix->s_topk, &ix->s_topk2, &ix->s_pass, &ix->s_filter,
                          &ix->s_visited, &ix->s_queue, &ix->s_tail, &ix->s_out_ids, &ix->s_out_dists,
-                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist, &ix->s_xnorm, &ix->s_qnorm, &ix->s_coarse, &ix->s_thr, &ix->s_cand, &ix->s_cand_cnt, &ix->s_bf16, &ix->s_qbf16};
+                         &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist, &ix->s_xnorm, &ix->s_qnorm, &ix->s_coarse, &ix->s_thr, &ix->s_cand, &ix->s_cand_cnt, &ix->s_bf16, &ix->s_qbf16, &ix->s_flags};
   for (auto* b : bufs) b->release();
   if (ix->h_out) cudaFreeHost(ix->h_out);
   for (auto& ev : ix->ev) if (ev) cudaEventDestroy(ev);
@@ -675,7 +676,15 @@ int eps_index_set_coarse(eps_index* h, int mode) {
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
   if (mode < 0 || mode > 2) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "coarse mode must be 0 (fp32), 1 (tf32) or 2 (bf16)");
+  if (mode != ix->coarse_mode) ix->coarse_boost = 1;  // the learnt k' multiplier belongs to one operand format
   ix->coarse_mode = mode;
+  return EPS_OK;
+}
+
+int eps_index_set_coarse_guard(eps_index* h, int on) {
+  Index* ix = reinterpret_cast<Index*>(h);
+  if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  ix->coarse_guard = on ? 1 : 0;
   return EPS_OK;
 }
 

@@ -30,7 +30,7 @@ class Stats(dict):
     def from_struct(cls, s):
         return cls(n_dist=int(s.n_dist), n_seed=int(s.n_seed), n_expand=int(s.n_expand), n_edges=int(s.n_edges),
                    n_queries=int(s.n_queries), kernel_ms=float(s.kernel_ms), total_ms=float(s.total_ms),
-                   kernel_launches=int(s.kernel_launches))
+                   kernel_launches=int(s.kernel_launches), n_redone=int(s.n_redone))
 
 
 class Index:
@@ -119,6 +119,10 @@ class Index:
     def set_coarse(self, mode):
         """0 = fp32 SIMT only, 1 = tcgen05 TF32 (default), 2 = tcgen05 bf16 mirror (exact re-score in all modes)."""
         check(self.L.eps_index_set_coarse(self.h, {"fp32": 0, "tf32": 1, "bf16": 2}.get(mode, mode)))
+
+    def set_coarse_guard(self, on=True):
+        """Verify the coarse pass after the re-score and redo unsafe queries (on by default)."""
+        check(self.L.eps_index_set_coarse_guard(self.h, int(bool(on))))
 
     # --- search ---
     def search(self, queries, limit, filter_nodes=None, want_stats=True):

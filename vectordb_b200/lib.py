@@ -9,7 +9,7 @@ _LIB = None
 EXPORTS = [
     "eps_index_create", "eps_index_destroy", "eps_index_sync_rows", "eps_index_adopt_device_rows", "eps_index_device_rows", "eps_index_rows",
     "eps_index_set_graph", "eps_index_build", "eps_index_get_graph", "eps_index_set_deleted", "eps_index_set_attrs", "eps_index_set_string_codes",
-    "eps_index_config", "eps_index_set_coarse", "eps_index_set_search_width", "eps_index_set_graph_tuning", "eps_search_batch", "eps_search_batch_device", "eps_merge_shards_device", "eps_facet_batch", "eps_shard_unique_id", "eps_shard_group_create", "eps_shard_group_destroy", "eps_search_batch_sharded", "eps_normalize",
+    "eps_index_config", "eps_index_set_coarse", "eps_index_set_coarse_guard", "eps_index_set_search_width", "eps_index_set_graph_tuning", "eps_search_batch", "eps_search_batch_device", "eps_merge_shards_device", "eps_facet_batch", "eps_shard_unique_id", "eps_shard_group_create", "eps_shard_group_destroy", "eps_search_batch_sharded", "eps_normalize",
     "eps_pair_distances", "eps_index_stream", "eps_last_error", "eps_version", "eps_device_count",
 ]
 
@@ -29,7 +29,7 @@ class FilterNode(C.Structure):
 class StatsStruct(C.Structure):
     _fields_ = [("n_dist", C.c_uint64), ("n_seed", C.c_uint64), ("n_expand", C.c_uint64), ("n_edges", C.c_uint64),
                 ("n_queries", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("n_redone", C.c_uint64)]
 
 
 class FacetSpec(C.Structure):
@@ -82,6 +82,7 @@ def load_library():
     L.eps_index_set_string_codes.argtypes = [vp, i32, i64, vp, i64]
     L.eps_index_config.argtypes = [vp, i64, i64, i32, i32]
     L.eps_index_set_coarse.argtypes = [vp, i32]
+    L.eps_index_set_coarse_guard.argtypes = [vp, i32]
     L.eps_index_set_search_width.argtypes = [vp, i32]
     L.eps_index_set_graph_tuning.argtypes = [vp, i32, i32]
     L.eps_search_batch.argtypes = [vp, vp, i64, i64, vp, i64, vp, vp, vp, vp]
