@@ -282,25 +282,32 @@ def run_reference_child(a, graph, L, queries, timeout, filter_str="", attr_mod=0
 
 
 def build_graph_for_reference(a, dev):
-    """Set-up of the reference arm: a CSR over the table.  On a GPU box it is built on the device by the library (the
-    reference's own build is infeasible at 10M rows); without a GPU (CPU contract test) the reference builds it
-    itself when the table is small; otherwise there is no graph and the reference takes its brute-force branch."""
+    """Set-up of the reference arm: a CSR over the table and the queue length to search it at.  On a GPU box the graph
+    is built on the device by the library (the reference's own build is infeasible at 10M rows) and L is found by the
+    same rule as in the GPU arm — the smallest L of --L-sweep whose recall@k against the exact scan reaches the
+    target — so both arms sit at the same operating point; without a GPU (CPU contract test) the reference builds the
+    graph itself when the table is small; otherwise there is no graph and the reference takes its brute-force branch."""
     import torch
     if torch.cuda.is_available():
-        import vectordb_b200
-        X = gen_table(a.rows, a.dim, a.dist, 42, dev, a.centers)
-        if a.metric == "cosine":
-            X /= X.norm(dim=1, keepdim=True)
-        ix = vectordb_b200.Index(a.metric, a.dim, capacity=a.rows, device=0)
-        ix.adopt_device_rows(X.data_ptr(), a.rows)
         t0 = time.perf_counter()
-        ix.build(a.rows, knn_k=a.knn_k, nnd_iters=a.nnd_iters)
+        A = Arena(a, a.dist, torch.device("cuda", 0), 0, 0, 1)
+        A.ground_truth()
+        A.ix.build(a.rows, knn_k=a.knn_k, nnd_iters=a.nnd_iters)
         torch.cuda.synchronize()
-        g = ix.get_graph()
-        ix.close()
-        del X
+        L = a.L
+        if not L:
+            for cand in [int(x) for x in a.L_sweep.split(",")]:
+                if cand > a.rows:
+                    break
+                L = cand
+                A.set_mode(("graph", cand, ""))
+                A.search(A.Qpool[0])
+                if recall_of(A.truth, A.out_ids, a.k) >= a.recall_target:
+                    break
+        g = A.ix.get_graph()
+        A.close()
         torch.cuda.empty_cache()
-        return g, "built on device by libepsilla_b200 in %.0f s (set-up, untimed)" % (time.perf_counter() - t0)
+        return g, L, "built on device by libepsilla_b200 (set-up, untimed, %.0f s incl. the L sweep)" % (time.perf_counter() - t0)
     if a.rows <= 200_000:
         from oracle import oracle
         if oracle.have_ref():
@@ -308,8 +315,8 @@ def build_graph_for_reference(a, dev):
             r = oracle.Ref(a.metric, a.dim, a.rows, [("ID", "int4")])
             r.set_rows(X)
             g = r.build(a.rows, threads=os.cpu_count() or 1)
-            return g, "built by the reference itself (RebuildThreads = %d)" % (os.cpu_count() or 1)
-    return None, "no graph: the reference's brute-force branch"
+            return g, a.L or 512, "built by the reference itself (RebuildThreads = %d)" % (os.cpu_count() or 1)
+    return None, a.L or 512, "no graph: the reference's brute-force branch"
 
 
 def run_reference_arm(a):
@@ -320,8 +327,7 @@ def run_reference_arm(a):
         return
     import torch
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    graph, how = build_graph_for_reference(a, dev)
-    L = a.L or 512
+    graph, L, how = build_graph_for_reference(a, dev)
     n_steps = a.warmup + a.steps
     Q = np.stack([gen_queries(a.batch, a.dim, a.dist, 43 + s * 64, dev, a.centers).cpu().numpy() for s in range(n_steps)])
     if a.metric == "cosine":
