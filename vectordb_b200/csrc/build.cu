@@ -317,15 +317,23 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
   std::vector<int32_t> h_ids(static_cast<size_t>(n) * stride), h_cnt(static_cast<size_t>(n));
   EPS_CUDA(cudaMemcpyAsync(h_ids.data(), ids2.p, h_ids.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
   EPS_CUDA(cudaMemcpyAsync(h_cnt.data(), cnt2.p, h_cnt.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+  std::vector<unsigned long long> h_knn(static_cast<size_t>(n) * K);
+  EPS_CUDA(cudaMemcpyAsync(h_knn.data(), knn.p, h_knn.size() * 8, cudaMemcpyDeviceToHost, ix->stream));
   EPS_CUDA(cudaStreamSynchronize(ix->stream));
   ids1.release(); dist1.release(); cnt1.release(); ids2.release(); dist2.release(); cnt2.release();
   rev.release(); rev_cnt.release(); knn.release();
 
-  // CheckConnectivity (nsg.cpp:687-775): flood from the navigation point; for the first unlinked vertex u, search
-  // the graph for u's own vector, attach u to the NEAREST ALREADY-LINKED vertex of the search pool, else to a RANDOM
-  // linked vertex; flood from u; repeat.  The searches are batched on device: the un-repaired graph is installed, the
-  // rows of all unlinked vertices go through graph_search (L2 like the rest of the refinement, beam = max(64,
-  // search_length)) and the attach / flood bookkeeping — integer work — runs on the host in the reference's order.
+  // CheckConnectivity (nsg.cpp:687-775): flood from the navigation point; for the first unlinked vertex u, attach u
+  // to the NEAREST ALREADY-LINKED vertex of a candidate pool, else to a RANDOM linked vertex; flood from u; repeat.
+  // The reference's pool is what a graph search for u's own vector evaluated.  Ours, in this order:
+  //   1. u's own kNN list (exact near neighbours, already on hand) — the nearest linked entry that has received
+  //      fewer than kRepairCap repair edges so far (on inner-product tables the kNN lists of most vertices point at
+  //      the same few large-norm rows; without the cap one of them collects O(n) repair edges);
+  //   2. the reference's own pool: the un-repaired graph is installed and the rows of the still unlinked vertices go
+  //      through graph_search on the device (L2 like the rest of the refinement, beam = max(64, search_length));
+  //   3. a random linked vertex (:767-774).
+  // The attach / flood bookkeeping — integer work — runs on the host in the reference's order.
+  constexpr size_t kRepairCap = 8;
   std::vector<std::vector<int32_t>> extra(static_cast<size_t>(n));  // edges added by the repair
   {
     std::vector<uint8_t> seen(static_cast<size_t>(n), 0);
@@ -347,6 +355,19 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
       }
     };
     flood(static_cast<int32_t>(nav));
+    for (int64_t u = 0; u < n && linked < n; ++u) {  // 1. nearest linked kNN entry with room
+      if (seen[u]) continue;
+      for (int j = 0; j < K; ++j) {
+        const unsigned long long key = h_knn[static_cast<size_t>(u) * K + j];
+        if ((key & kKeyMask) == kKeyInf) break;
+        const int32_t w = static_cast<int32_t>(key_id(key));
+        if (seen[w] && extra[w].size() < kRepairCap) {
+          extra[w].push_back(static_cast<int32_t>(u));
+          flood(static_cast<int32_t>(u));
+          break;
+        }
+      }
+    }
     if (linked < n) {
       std::vector<int32_t> unl;
       for (int64_t v = 0; v < n; ++v) if (!seen[v]) unl.push_back(static_cast<int32_t>(v));
