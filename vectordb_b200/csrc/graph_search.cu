@@ -33,6 +33,7 @@
 // wide mode (width W = 2/4/8): up to W candidates are picked per iteration from queue ∪ pending while the rows
 //   of the previous iteration are still in flight — the device analogue of IntraQueryThreads > 1; like that
 //   mode it is not bit-identical to the sequential order.
+#include <cstdio>
 #include <cstdlib>
 
 #include "async.cuh"
@@ -47,6 +48,16 @@ constexpr int kPC = 128;        // accepted keys pending their merge (= one key 
 constexpr int kFC = 1024;       // fresh-id FIFO capacity at W = 8 (power of two >= kMaxW * kEll + kMaxR + kGsThreads)
 constexpr int kMaxR = 32;       // ring slots (upper bound; one issuing lane per slot)
 constexpr int kRounds = kMaxW * kEll / kGsThreads;  // adjacency slots per thread
+
+// Developer build only (make EXTRA=-DEPS_GS_PROFILE): per-phase cycle counters of warp 0 (pick / adjacency / merge /
+// barrier waits) and of warp 1 (row wait / row math), summed over CTAs into stats[8..15].  Compiled out otherwise.
+#ifdef EPS_GS_PROFILE
+#define GS_T(var) const long long var = clock64()
+#define GS_ACC(slot, t0, t1) do { if (lane == 0) prof[slot] += (t1) - (t0); } while (0)
+#else
+#define GS_T(var) do {} while (0)
+#define GS_ACC(slot, t0, t1) do {} while (0)
+#endif
 
 struct GSArgs {
   const float* vectors;
@@ -208,6 +219,10 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
   uint32_t par[2] = {0u, 0u};
   int sid[2] = {0, 0};
   unsigned long long st_ndist = 0, st_nexp = 0, st_nedge = 0;
+#ifdef EPS_GS_PROFILE
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 0 barrier X, 1 merge, 2 row wait, 3 row math, 4 pick, 5 barrier 1, 6 adjacency+visited, 7 barrier 2 + FIFO
+  const long long t_kernel0 = clock64();
+#endif
 
   for (;;) {
     __syncthreads();
@@ -238,13 +253,18 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     for (;;) {
       // barrier X: pending appends, FIFO writes and slot states of the previous iteration are settled;
       // the count is the number of ring slots with a row in flight
+      GS_T(tx0);
       const int inflight = __syncthreads_count((tl == 0 && occ[0]) || (tl == 1 && occ[1]));
+      GS_T(tx1);
+      GS_ACC(0, tx0, tx1);
       const int m = s_npend;
       const uint32_t head = s_head;
       const int ncont = s_ncont;
       // -- D: merge the pending keys (every time in exact mode; when the buffer could overflow otherwise) --
       const bool merged = m > 0 && (a.exact || m > kPC - R);
       if (merged) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor);
+      GS_T(tm1);
+      GS_ACC(1, tx1, tm1);
       const bool idle = inflight == 0 && head == fifo_tail;
       // A runs when the ring cannot be kept full from the backlog alone (wide) / when the previous expansion
       // has been consumed and merged (exact)
@@ -260,7 +280,10 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
             if (occ[j]) {
               float p;
               if (staged) {
+                GS_T(tw0);
                 mbar_wait(bar0 + 8 * slot, par[j]);
+                GS_T(tw1);
+                GS_ACC(2, tw0, tw1);
                 par[j] ^= 1u;
                 const float4* row = reinterpret_cast<const float4*>(ring + static_cast<size_t>(slot) * a.slot_bytes);
                 p = a.metric == EPS_METRIC_L2 ? team_partial_vec4<true>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl)
@@ -278,6 +301,8 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
               }
               occ[j] = false;
             }
+            GS_T(tc1);
+            GS_ACC(3, tm1, tc1);  // team phase so far (row wait included; subtract slot 2)
             unsigned idx = 0;
             if (tl == 0) {
               idx = atomicAdd(&s_head, 1u);
@@ -298,6 +323,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
         }
       }
       if (!want) continue;
+      GS_T(tp0);
 
       // -- A0: pick up to W unchecked candidates, smallest first, from queue ∪ pending (warp 0) --
       if (warp == 0) {
@@ -359,7 +385,11 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
         }
         if (lane == 0) s_ncur = cnt;
       }
+      GS_T(tp1);
+      GS_ACC(4, tp0, tp1);
       __syncthreads();  // (1)
+      GS_T(tb1);
+      GS_ACC(5, tp1, tb1);
       const int ncur = s_ncur;
       if (ncur == 0 && ncont == 0) {
         if (idle) break;  // nothing unchecked in queue ∪ pending, nothing in flight, nothing queued: done
@@ -398,6 +428,8 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
         const unsigned vb = __ballot_sync(kFull, nb[r] >= 0);
         if (lane == 0) { s_wcnt[r][warp] = __popc(bal[r]); st_nedge += static_cast<unsigned long long>(__popc(vb)); }
       }
+      GS_T(ta1);
+      GS_ACC(6, tb1, ta1);
       __syncthreads();  // (2)
       int total = 0;
 #pragma unroll
@@ -434,6 +466,8 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
         if (tid == 0) st_nexp += static_cast<unsigned long long>(ncur);
       }
       if (tid == 0) st_ndist += static_cast<unsigned long long>(total);
+      GS_T(tf1);
+      GS_ACC(7, ta1, tf1);
     }
 
     // ---- results + visited reset (:711-714) ----
@@ -450,6 +484,12 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       for (int64_t i = tid; i < n4; i += kGsThreads) v4[i] = z;
     }
   }
+#ifdef EPS_GS_PROFILE
+  if (lane == 0 && warp < 2) {
+    for (int i = 0; i < 8; ++i) atomicAdd(&a.stats[8 + warp * 8 + i], static_cast<unsigned long long>(prof[i]));
+    if (warp == 0) atomicAdd(&a.stats[24], static_cast<unsigned long long>(clock64() - t_kernel0));
+  }
+#endif
   if (st_ndist) atomicAdd(&a.stats[0], st_ndist);
   if (st_nexp) atomicAdd(&a.stats[1], st_nexp);
   if (st_nedge) atomicAdd(&a.stats[2], st_nedge);
@@ -562,13 +602,15 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
     ix->visited_slots = slots;
   }
   // bitmaps must start clean; the kernel leaves them clean.  (Re)zero when the geometry changed.
-  if (ix->vis_clean_ptr != ix->s_visited.p || ix->vis_clean_words != words) {
+  // (a re-grown buffer may come back at the old address: the capacity is part of the geometry)
+  if (ix->vis_clean_ptr != ix->s_visited.p || ix->vis_clean_words != words || ix->vis_clean_cap != ix->s_visited.cap) {
     EPS_CUDA(cudaMemsetAsync(ix->s_visited.p, 0, ix->s_visited.cap, ix->stream));
     ix->vis_clean_ptr = ix->s_visited.p;
     ix->vis_clean_words = words;
+    ix->vis_clean_cap = ix->s_visited.cap;
   }
-  EPS_TRY(ix->s_misc.reserve(64));
-  EPS_CUDA(cudaMemsetAsync(ix->s_misc.p, 0, 64, ix->stream));
+  EPS_TRY(ix->s_misc.reserve(256));  // [0..3] counters, [+32 B] work counter, [8..24] developer phase timers
+  EPS_CUDA(cudaMemsetAsync(ix->s_misc.p, 0, 256, ix->stream));
   uint64_t launches = 1;
   if (!ix->d_ell) {  // fixed-stride adjacency, built once per installed graph
     EPS_CUDA(cudaMalloc(&ix->d_ell, static_cast<size_t>(ix->n_indexed) * kEll * 4));
@@ -617,6 +659,16 @@ int read_graph_counters(Index* ix, eps_stats* stats) {
   stats->n_dist += h[0];
   stats->n_expand += h[1];
   stats->n_edges += h[2];
+#ifdef EPS_GS_PROFILE
+  unsigned long long pr[32];
+  EPS_CUDA(cudaMemcpy(pr, ix->s_misc.p, 256, cudaMemcpyDeviceToHost));
+  const char* names[8] = {"barrierX", "merge", "row_wait", "team_phase", "pick", "barrier1", "adj+visited", "barrier2+fifo"};
+  const double tot = static_cast<double>(pr[24]) + 1.0;
+  fprintf(stderr, "[gs-profile] kernel cycles summed over CTAs %.3e;", tot);
+  for (int w = 0; w < 2; ++w)
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " w%d.%s=%.1f%%", w, names[i], 100.0 * static_cast<double>(pr[8 + w * 8 + i]) / tot);
+  fprintf(stderr, "\n");
+#endif
   return EPS_OK;
 }
 

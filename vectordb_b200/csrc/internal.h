@@ -90,6 +90,7 @@ struct Index {
   int64_t visited_slots = 0;
   const void* vis_clean_ptr = nullptr;  // geometry for which the visited bitmaps are known to be zero
   int64_t vis_clean_words = 0;
+  size_t vis_clean_cap = 0;
   bool graph_counters_pending = false;
   void* h_out = nullptr;         // pinned host mirror of the packed result block (eps_search_batch)
   size_t h_out_cap = 0;

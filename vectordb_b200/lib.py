@@ -45,7 +45,8 @@ class BuildParams(C.Structure):
 
 
 def library_path():
-    return os.path.join(HERE, "libepsilla_b200.so")
+    # EPS_B200_LIB: developer override (e.g. the phase-timer build `make -C vectordb_b200/csrc prof`)
+    return os.environ.get("EPS_B200_LIB") or os.path.join(HERE, "libepsilla_b200.so")
 
 
 def build_library(verbose=False):
