@@ -153,7 +153,7 @@ EPS_API int eps_index_set_string_codes(eps_index* ix, int column, int64_t first_
 EPS_API int eps_index_config(eps_index* ix, int64_t L_master, int64_t L_local, int prefilter, int force_brute);
 
 /* Graph-search expansion width: how many unchecked queue entries are expanded per iteration.  1 (default)
- * reproduces the reference at IntraQueryThreads = 1 exactly; 2 / 4 / 8 are the device analogue of the reference's
+ * reproduces the reference at IntraQueryThreads = 1 exactly; 2 .. 8 are the device analogue of the reference's
  * IntraQueryThreads > 1 (config.hpp:18, default 4): candidates expanded in parallel against a slightly stale
  * bound — higher throughput, results not bit-identical to the sequential order (as in the reference). */
 EPS_API int eps_index_set_search_width(eps_index* ix, int width);

@@ -656,8 +656,7 @@ int eps_pair_distances(int device, int metric, const float* a, const float* b, i
 int eps_index_set_search_width(eps_index* h, int width) {
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
-  if (width != 1 && width != 2 && width != 4 && width != 8)
-    return eps::fail(EPS_ERR_INVALID_ARGUMENT, "search width must be 1, 2, 4 or 8");
+  if (width < 1 || width > 8) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "search width must be in [1, 8]");
   ix->search_width = width;
   return EPS_OK;
 }

@@ -45,7 +45,6 @@ constexpr int kEll = 64;        // adjacency ids per fixed-stride row
 constexpr int kGsThreads = 128;
 constexpr int kMaxW = 8;        // candidates picked per iteration (upper bound)
 constexpr int kPC = 128;        // accepted keys pending their merge (= one key per thread in the merge)
-constexpr int kFC = 1024;       // fresh-id FIFO capacity at W = 8 (power of two >= kMaxW * kEll + kMaxR + kGsThreads)
 constexpr int kMaxR = 32;       // ring slots (upper bound; one issuing lane per slot)
 constexpr int kRounds = kMaxW * kEll / kGsThreads;  // adjacency slots per thread
 
@@ -582,7 +581,8 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   const bool staged = ix->vec4;  // 16-byte aligned rows of a multiple of 16 bytes: eligible for bulk async copies
   const int slot_bytes = staged ? dim * 4 : 0;
   int R = ring_slots_for(ix, slot_bytes);
-  const int fc = width > 4 ? kFC : kFC / 2;  // backlog below R + W * kEll new ids + one continuation chunk
+  // FIFO: a backlog below R entries + the ids one A step appends (W adjacency rows or one 128-id continuation chunk)
+  const int fc = next_pow2(std::max(width * kEll, kGsThreads) + kMaxR);
   auto smem_for = [&](int r) {
     return static_cast<size_t>(r) * slot_bytes + static_cast<size_t>(Lp) * 8 + 2 * kPC * 8 + kMaxR * 8 +
            static_cast<size_t>(dimp) * 4 + kPC * 4 + static_cast<size_t>(fc) * 4;
