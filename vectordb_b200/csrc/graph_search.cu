@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       const int ncont = s_ncont;
       // -- D: merge the pending keys (every time in exact mode; when the buffer could overflow otherwise) --
       const bool merged = m > 0 && (a.exact || m > kPC - R);
+      // s_npend / s_head are bumped by the team phase below: no thread may get there before EVERY thread has taken
+      // the snapshot above (the merge's own barriers do that when there is a merge)
       if (merged) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor);
+      else __syncthreads();
       GS_T(tm1);
       GS_ACC(1, tx1, tm1);
       const bool idle = inflight == 0 && head == fifo_tail;
