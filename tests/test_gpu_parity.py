@@ -203,7 +203,7 @@ def test_empty_and_edge_cases(vdb):
     ids, ds, cnt, _ = ix.search(X[0], 5)
     assert cnt[0] == 0
     with pytest.raises(vdb.EpsError):
-        ix.search(X[0], 5, filter_nodes=np.array([[2, 0, -1, -1, 0, 0, 0, -1]], np.int64))  # StringConst: out of scope
+        ix.search(X[0], 5, filter_nodes=np.array([[29, 3, 0, 0, 0, 0, 0, -1]], np.int64))  # LIKE: out of scope (and malformed)
     ix.close()
 
 
@@ -389,7 +389,8 @@ def test_nn_descent_build_quality(vdb, m):
         ix.build(n, exact_knn_below=below, knn_k=64)
         ni, off, nb, nav = ix.get_graph()
         deg = np.diff(off)
-        assert ni == n and deg.min() >= 1 and deg.max() <= 4 * 50, (name, deg.max())
+        others = np.delete(deg, nav)  # the navigation point also carries the entries of otherwise unreachable components
+        assert ni == n and deg.min() >= 1 and others.max() <= 50 + 16 and deg[nav] <= 50 + 4096, (name, others.max(), deg[nav])
         ix.config(200, 200)
         ix.set_search_width(1)
         ids, _, _, st = ix.search(Q, 10)
@@ -427,7 +428,7 @@ def test_build_repair_does_not_grow_hubs(vdb):
     ix.build(n, knn_k=64, nnd_iters=8)
     ni, off, nb, nav = ix.get_graph()
     deg = np.diff(off)
-    assert deg.max() <= 4 * 50, deg.max()
+    assert np.delete(deg, nav).max() <= 50 + 16 and deg[nav] <= 50 + 4096, (np.delete(deg, nav).max(), deg[nav])
     # every vertex reachable from the navigation point
     seen = np.zeros(n, bool)
     seen[nav] = True
@@ -628,27 +629,32 @@ def test_facets_match_reference(vdb, have_ref):
 
 
 def test_exact_scan_guard_catches_a_coarse_pass_that_cannot_rank(vdb):
-    """Weak point 1 of round 1: exactness of the tensor-core scan must be enforced, not hoped for.  On a table whose
-    rows differ by far less than a bf16 rounding step the coarse pass cannot rank anything; the guard (exact k-th best
-    + 2 x the batch's largest observed coarse error must not exceed the coarse k'-th threshold) has to notice and the
-    answer must still be the fp32 scan's.  On ordinary data the guard stays silent."""
+    """Weak point 1 of round 1: exactness of the tensor-core scan must be enforced, not hoped for.  300 rows of an
+    ordinary table form a bundle around the queries whose members differ by far less than a bf16 rounding step: the
+    coarse pass ranks the bundle ahead of everything else but cannot rank INSIDE it, so a 128-entry candidate list holds
+    a random subset of it.  The guard (exact k-th best + 2 x the batch's largest observed coarse error must not exceed
+    the coarse k'-th threshold) has to notice and the answer must be the fp32 scan's.  On ordinary data it stays silent."""
     n, d, nq, k = 100000, 64, 128, 10
     rng = np.random.default_rng(7)
-    base = rng.random(d, dtype=np.float32)
-    X = (base[None, :] + 1e-3 * rng.standard_normal((n, d))).astype(np.float32)
-    Q = (base[None, :] + 1e-3 * rng.standard_normal((nq, d))).astype(np.float32)
+    X = gen(n, d, 6)
+    centre = rng.random(d, dtype=np.float32)
+    where = rng.choice(n, 300, replace=False)
+    X[where] = (centre[None, :] + 1e-3 * rng.standard_normal((300, d))).astype(np.float32)
+    Q = (centre[None, :] + 1e-3 * rng.standard_normal((nq, d))).astype(np.float32)
     ix = vdb.Index("l2", d, host_vectors=X)
     ix.sync_rows(n)
     ix.config(500, 500, force_brute=True)
     ix.set_coarse("fp32")
     want, wd, _, _ = ix.search(Q, k)
+    assert np.isin(want, where).all()
     for mode in ("bf16", "tf32"):
         ix.set_coarse(mode)
         got, gd, _, st = ix.search(Q, k)
-        assert st["n_redone"] > 0, mode
         assert np.allclose(gd, wd, rtol=1e-5) and (got == want).mean() > 0.999, mode
+        if mode == "bf16":
+            assert st["n_redone"] > 0
     ix.set_coarse_guard(False)                    # the unguarded pass really is wrong here: the test has teeth
-    ix.set_coarse("bf16")
+    ix.set_coarse("bf16")                         # (set_coarse to another mode and back resets the learnt k')
     raw, _, _, st0 = ix.search(Q, k)
     assert st0["n_redone"] == 0 and (raw == want).mean() < 0.9
     ix.close()

@@ -624,8 +624,10 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     EPS_CUDA(cudaMemcpyAsync(h_state, d_overflow, 8, cudaMemcpyDeviceToHost, ix->stream));
     EPS_CUDA(cudaStreamSynchronize(ix->stream));
     if (stats) stats->kernel_launches += launches;
-    if (h_state[0])  // never silently truncated: the call is redone on the fp32 path
+    if (h_state[0]) {  // never silently truncated: the call is redone on the fp32 path
+      if (stats) stats->n_redone += static_cast<uint64_t>(nq);
       return topk_impl(ix, d_queries, nq, row_start, row_end, k_final, d_prog, h_prog, prefilter, self_base, d_final, stats, false);
+    }
     if (guard && h_state[1] > 0) {
       const int64_t n_bad = h_state[1];
       if (n_bad > std::max<int64_t>(8, nq / 32) && k < 4096) {

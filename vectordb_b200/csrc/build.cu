@@ -325,15 +325,20 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
 
   // CheckConnectivity (nsg.cpp:687-775): flood from the navigation point; for the first unlinked vertex u, attach u
   // to the NEAREST ALREADY-LINKED vertex of a candidate pool, else to a RANDOM linked vertex; flood from u; repeat.
-  // The reference's pool is what a graph search for u's own vector evaluated.  Ours, in this order:
-  //   1. u's own kNN list (exact near neighbours, already on hand) — the nearest linked entry that has received
-  //      fewer than kRepairCap repair edges so far (on inner-product tables the kNN lists of most vertices point at
-  //      the same few large-norm rows; without the cap one of them collects O(n) repair edges);
-  //   2. the reference's own pool: the un-repaired graph is installed and the rows of the still unlinked vertices go
+  // The reference's pool is what a graph search for u's own vector evaluated; its selection pools come from searches
+  // that START at the navigation point, which is what makes its graph navigable from there.  Ours are kNN lists, so
+  // on clustered data whole clusters are separate components; the repair has to give each of them an entry the search
+  // can find.  In this order:
+  //   1. u's own kNN list (exact near neighbours, already on hand): the nearest linked entry that has received fewer
+  //      than kRepairCap repair edges so far (on inner-product tables the kNN lists of most vertices point at the same
+  //      few large-norm rows; without the cap one of them collects O(n) repair edges);
+  //   2. NO kNN entry of u is linked: u's neighbourhood is a component of its own — u becomes an out-neighbour of the
+  //      navigation point, i.e. part of every search's seed set (PrepareInitIds starts from those), up to kNavCap;
+  //   3. the reference's own pool: the un-repaired graph is installed and the rows of the still unlinked vertices go
   //      through graph_search on the device (L2 like the rest of the refinement, beam = max(64, search_length));
-  //   3. a random linked vertex (:767-774).
+  //   4. a random linked vertex (:767-774).
   // The attach / flood bookkeeping — integer work — runs on the host in the reference's order.
-  constexpr size_t kRepairCap = 8;
+  constexpr size_t kRepairCap = 16, kNavCap = 4096;
   std::vector<std::vector<int32_t>> extra(static_cast<size_t>(n));  // edges added by the repair
   {
     std::vector<uint8_t> seen(static_cast<size_t>(n), 0);
@@ -355,17 +360,24 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
       }
     };
     flood(static_cast<int32_t>(nav));
-    for (int64_t u = 0; u < n && linked < n; ++u) {  // 1. nearest linked kNN entry with room
+    for (int64_t u = 0; u < n && linked < n; ++u) {
       if (seen[u]) continue;
-      for (int j = 0; j < K; ++j) {
+      bool any_linked = false, done = false;
+      for (int j = 0; j < K && !done; ++j) {  // 1. nearest linked kNN entry with room
         const unsigned long long key = h_knn[static_cast<size_t>(u) * K + j];
         if ((key & kKeyMask) == kKeyInf) break;
         const int32_t w = static_cast<int32_t>(key_id(key));
-        if (seen[w] && extra[w].size() < kRepairCap) {
+        if (!seen[w]) continue;
+        any_linked = true;
+        if (extra[w].size() < kRepairCap) {
           extra[w].push_back(static_cast<int32_t>(u));
           flood(static_cast<int32_t>(u));
-          break;
+          done = true;
         }
+      }
+      if (!done && !any_linked && extra[nav].size() < kNavCap) {  // 2. a component of its own: entry from the seed set
+        extra[nav].push_back(static_cast<int32_t>(u));
+        flood(static_cast<int32_t>(u));
       }
     }
     if (linked < n) {
