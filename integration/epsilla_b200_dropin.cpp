@@ -62,11 +62,17 @@ struct Mirror {
   struct Pending {
     const float* query;
     size_t limit;
-    const std::vector<eps_filter_node>* nodes;  // lowered filter program (empty = none); equal programs share a launch
+    const std::vector<query::expr::ExprNodePtr>* filter;  // the caller's parsed filter (empty = none)
+    std::string key;                  // serialised filter: requests with equal keys (and limits) share a launch
+    TableSegmentMVP* segment;
+    int64_t total;                    // record_number_ snapshot of the caller (:839)
+    int64_t n_indexed;
+    int num_threads;
     int64_t* ids;
     double* dists;
     int64_t count = 0;
     int rc = EPS_OK;
+    bool unsupported = false;         // report NOT_IMPLEMENTED_ERROR instead of DB_UNEXPECTED_ERROR
     std::string err;  // eps_last_error() is thread-local: the leader copies the text for its followers
     bool done = false;
   };
@@ -114,85 +120,225 @@ static int MetricOf(const DistFunc& f) {
   return -1;  // a DistFunc the library does not know (e.g. a test wrapper)
 }
 
-static Status Fail(const char* what) {
-  return Status(DB_UNEXPECTED_ERROR, std::string("epsilla_b200: ") + what + ": " + eps_last_error());
+// Device ordinal of the mirrors: EPSILLA_B200_DEVICE (the reference has no GPU setting to read it from).
+static int DeviceOrdinal() {
+  static const int dev = [] { const char* e = std::getenv("EPSILLA_B200_DEVICE"); return e ? std::atoi(e) : 0; }();
+  return dev;
 }
 
-static bool SameProgram(const std::vector<eps_filter_node>& a, const std::vector<eps_filter_node>& b) {
-  return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(eps_filter_node)) == 0);
+// Byte-exact serialisation of a parsed filter: equal strings <=> the same program on the same columns.
+static std::string FilterKey(const std::vector<query::expr::ExprNodePtr>& nodes) {
+  std::string k;
+  auto put = [&](const void* p, size_t n) { k.append(static_cast<const char*>(p), n); };
+  for (const auto& np : nodes) {
+    const auto& n = *np;
+    const int64_t head[5] = {static_cast<int64_t>(n.node_type), static_cast<int64_t>(n.value_type), static_cast<int64_t>(n.left),
+                             static_cast<int64_t>(n.right), n.int_value};
+    put(head, sizeof(head));
+    put(&n.double_value, sizeof(double));
+    k.push_back(n.bool_value ? 1 : 0);
+    for (const std::string* sp : {&n.field_name, &n.str_value, &n.function_name}) {
+      const uint32_t len = static_cast<uint32_t>(sp->size());
+      put(&len, 4);
+      k.append(*sp);
+    }
+    const uint32_t na = static_cast<uint32_t>(n.arguments.size());
+    put(&na, 4);
+    for (size_t a : n.arguments) { const int64_t v = static_cast<int64_t>(a); put(&v, 8); }
+  }
+  return k;
 }
 
-// Leader/follower batch former.  The first caller becomes the leader and serves, in ONE eps_search_batch call,
-// every request queued at that moment with the same limit and the same filter program; requests that arrive
-// while a launch is in flight queue up and form the next batch, so a lone caller never waits and concurrent
-// callers are batched by the device's own service time.  Requests keep their per-call semantics (one query,
-// own result arrays); only the launch is shared.
-static int SearchCoalesced(Mirror* m, const float* query, size_t limit, const std::vector<eps_filter_node>& nodes, int64_t* ids,
-                           double* dists, int64_t* count, std::string* err) {
-  Mirror::Pending me;
-  me.query = query; me.limit = limit; me.nodes = &nodes; me.ids = ids; me.dists = dists;
+// Segment state -> device mirror, once per launch (caller holds m->mu): lazily create the index, upload appended
+// rows, ship the dirty span of the deleted bitset.
+static int Prepare(Mirror* m, TableSegmentMVP* seg, int64_t total, int64_t n_indexed, int num_threads) {
+  if (m->ix == nullptr) {
+    m->capacity = static_cast<int64_t>(seg->size_limit_);
+    if (eps_index_create(&m->ix, m->metric, m->dim, m->host_vectors, m->capacity, DeviceOrdinal()) != EPS_OK) return -1;
+    if (eps_index_sync_rows(m->ix, std::max<int64_t>(total, n_indexed)) != EPS_OK) return -1;
+    if (n_indexed > 0 && eps_index_set_graph(m->ix, n_indexed, m->offsets, m->nbrs, m->nav) != EPS_OK) return -1;
+    if (eps_index_config(m->ix, m->L_master, m->L_local, m->prefilter ? 1 : 0, 0) != EPS_OK) return -1;
+    // IntraQueryThreads (config.hpp:18, default 4): 1 = the sequential order, > 1 = that many candidates expanded
+    // concurrently (the reference's parallel mode is itself not a pure function of its inputs)
+    const int width = num_threads >= 8 ? 8 : num_threads >= 4 ? 4 : num_threads >= 2 ? 2 : 1;
+    if (eps_index_set_search_width(m->ix, width) != EPS_OK) return -1;
+  }
+  if (total > eps_index_rows(m->ix) && eps_index_sync_rows(m->ix, total) != EPS_OK) return -1;
+  ConcurrentBitset& deleted = *(seg->deleted_);  // (:840)
+  const int64_t rows = eps_index_rows(m->ix);
+  if (eps_index_set_deleted(m->ix, deleted.data(), (rows + 7) / 8) != EPS_OK) return -1;
+  return 0;
+}
+
+// filter nodes -> PODs (:841-848), caller holds m->mu: field names resolved through the segment's offset map; string
+// work happens here, on the host — new rows of the string columns a filter reads are dictionary-encoded and appended
+// to the device mirror, literals become codes, `x IN (a, b, ..)` becomes `x = a OR x = b ..`.
+// Returns 0, -1 (library error, text in eps_last_error) or -2 (out of scope, text in *why).
+static int LowerFilter(Mirror* m, TableSegmentMVP* seg, const std::vector<query::expr::ExprNodePtr>& src,
+                       std::vector<eps_filter_node>* out, std::string* why) {
+  using query::expr::NodeType;
+  using query::expr::ValueType;
+  out->clear();
+  if (src.empty()) return 0;
+  const int64_t rows = eps_index_rows(m->ix);
+  if (m->attr_rows != rows || m->attr_ptr != seg->attribute_table_) {
+    if (eps_index_set_attrs(m->ix, seg->attribute_table_, seg->primitive_offset_, rows) != EPS_OK) return -1;
+    m->attr_rows = rows;
+    m->attr_ptr = seg->attribute_table_;
+  }
+  for (const auto& np : src) {
+    if (np->node_type != NodeType::StringAttr) continue;
+    auto it = seg->field_name_mem_offset_map_.find(np->field_name);
+    if (it == seg->field_name_mem_offset_map_.end()) continue;
+    const size_t col = it->second;
+    if (col >= 8 || col >= seg->var_len_attr_table_.size()) { *why = "more than 8 string columns are out of scope of the GPU path"; return -2; }
+    if (m->str_rows.size() <= col) m->str_rows.resize(col + 1, 0);
+    if (m->str_rows[col] < rows) {
+      std::vector<int32_t> codes;
+      codes.reserve(static_cast<size_t>(rows - m->str_rows[col]));
+      auto& column = seg->var_len_attr_table_[col];
+      for (int64_t r = m->str_rows[col]; r < rows; ++r) {
+        const std::string* sv = std::get_if<std::string>(&column[r]);
+        auto ins = m->dict.emplace(sv ? *sv : std::string(), static_cast<int32_t>(m->dict.size()));
+        codes.push_back(ins.first->second);
+      }
+      if (eps_index_set_string_codes(m->ix, static_cast<int>(col), m->str_rows[col], codes.data(), static_cast<int64_t>(codes.size())) != EPS_OK)
+        return -1;
+      m->str_rows[col] = rows;
+    }
+  }
+  std::vector<int64_t> remap(src.size(), -1);  // parser index -> index of the POD holding the node's value
+  auto pod = [](NodeType t, ValueType v) {
+    eps_filter_node d;
+    std::memset(&d, 0, sizeof(d));
+    d.node_type = static_cast<int64_t>(t);
+    d.value_type = static_cast<int64_t>(v);
+    d.left = d.right = -1;
+    d.field_offset = -1;
+    return d;
+  };
+  for (size_t i = 0; i < src.size(); ++i) {
+    const auto& sn = *src[i];
+    if (sn.node_type == NodeType::IN) {  // expr_evaluator.cpp:176-185: last argument is the attribute
+      const size_t len = sn.arguments.size();
+      if (len < 2) { *why = "malformed IN node"; return -2; }
+      const int64_t attr = remap[sn.arguments[len - 1]];
+      int64_t acc = -1;
+      for (size_t j = 0; j + 1 < len; ++j) {
+        eps_filter_node eq = pod(NodeType::EQ, ValueType::BOOL);
+        eq.left = attr;
+        eq.right = remap[sn.arguments[j]];
+        out->push_back(eq);
+        const int64_t eq_at = static_cast<int64_t>(out->size()) - 1;
+        if (acc < 0) { acc = eq_at; continue; }
+        eps_filter_node o = pod(NodeType::OR, ValueType::BOOL);
+        o.left = acc;
+        o.right = eq_at;
+        out->push_back(o);
+        acc = static_cast<int64_t>(out->size()) - 1;
+      }
+      remap[i] = acc;
+      continue;
+    }
+    if (sn.node_type == NodeType::Add && sn.value_type == ValueType::STRING) { *why = "string concatenation in filters is out of scope of the GPU path"; return -2; }
+    eps_filter_node d = pod(sn.node_type, sn.value_type);
+    const bool unary = sn.node_type == NodeType::NOT;
+    const bool leaf = sn.node_type <= NodeType::GeoPointAttr;
+    if (!leaf) {
+      d.left = sn.left < src.size() ? remap[sn.left] : -1;
+      d.right = (!unary && sn.right < src.size()) ? remap[sn.right] : -1;
+    }
+    d.int_value = sn.int_value;
+    d.double_value = sn.double_value;
+    d.bool_value = sn.bool_value ? 1 : 0;
+    if (sn.node_type == NodeType::StringConst) {
+      auto it = m->dict.find(sn.str_value);
+      d.int_value = it == m->dict.end() ? -1 : it->second;  // a literal no row carries equals nothing
+    }
+    if (!sn.field_name.empty()) {
+      if (sn.field_name == "@distance") d.field_offset = -2;
+      else {
+        auto it = seg->field_name_mem_offset_map_.find(sn.field_name);
+        if (it != seg->field_name_mem_offset_map_.end()) d.field_offset = static_cast<int64_t>(it->second);
+      }
+    }
+    out->push_back(d);
+    remap[i] = static_cast<int64_t>(out->size()) - 1;
+  }
+  return 0;
+}
+
+// Leader/follower batch former.  A caller only enqueues its request (no device work, no mirror lock); the first
+// caller becomes the leader and serves, in ONE eps_search_batch call, every request queued at that moment with the
+// same limit and the same filter — mirroring the segment (appended rows, dirty delete bytes, new string codes) and
+// lowering the filter once per launch.  Requests that arrive while a launch is in flight queue up and form the next
+// batch, so a lone caller never waits and concurrent callers are batched by the device's own service time.
+// Requests keep their per-call semantics (one query, own result arrays); only the launch is shared.
+static void SearchCoalesced(Mirror* m, Mirror::Pending* me) {
   std::unique_lock<std::mutex> q(m->qmu);
-  m->waiting.push_back(&me);
+  m->waiting.push_back(me);
   if (m->leader_active) {
-    m->qcv.wait(q, [&] { return me.done || !m->leader_active; });
-    if (me.done) { *count = me.count; *err = me.err; return me.rc; }
+    m->qcv.wait(q, [&] { return me->done || !m->leader_active; });
+    if (me->done) return;
     // the leader left before taking this request: fall through and lead
   }
   m->leader_active = true;
-  while (!me.done) {
+  while (!me->done) {
     std::vector<Mirror::Pending*> batch;
     std::vector<Mirror::Pending*> rest;
     Mirror::Pending* head = m->waiting.front();
-    for (auto* p : m->waiting) ((p->limit == head->limit && SameProgram(*p->nodes, *head->nodes)) ? batch : rest).push_back(p);
+    for (auto* p : m->waiting)
+      ((p->limit == head->limit && p->segment == head->segment && p->key == head->key) ? batch : rest).push_back(p);
     m->waiting.swap(rest);
     q.unlock();
     const size_t lim = head->limit;
     const int64_t nq = static_cast<int64_t>(batch.size());
-    int rc;
+    int rc = EPS_OK;
+    bool unsupported = false;
     std::string text;
-    if (nq == 1) {  // no copy through staging buffers for a lone request
-      std::lock_guard<std::mutex> lk(m->mu);
-      rc = eps_search_batch(m->ix, head->query, 1, static_cast<int64_t>(lim), head->nodes->empty() ? nullptr : head->nodes->data(),
-                            static_cast<int64_t>(head->nodes->size()), head->ids, head->dists, &head->count, nullptr);
-      if (rc != EPS_OK) text = eps_last_error();
-      ++m->launches; ++g_launches;
-    } else {
-      std::vector<float> qbuf(static_cast<size_t>(nq) * m->dim);
-      for (int64_t i = 0; i < nq; ++i) std::memcpy(qbuf.data() + i * m->dim, batch[i]->query, sizeof(float) * m->dim);
-      std::vector<int64_t> oi(static_cast<size_t>(nq) * lim), oc(static_cast<size_t>(nq));
-      std::vector<double> od(static_cast<size_t>(nq) * lim);
-      {
-        std::lock_guard<std::mutex> lk(m->mu);  // the index itself is single-threaded
-        rc = eps_search_batch(m->ix, qbuf.data(), nq, static_cast<int64_t>(lim), head->nodes->empty() ? nullptr : head->nodes->data(),
-                              static_cast<int64_t>(head->nodes->size()), oi.data(), od.data(), oc.data(), nullptr);
-        if (rc != EPS_OK) text = eps_last_error();
-        ++m->launches; ++g_launches;
+    {
+      std::lock_guard<std::mutex> lk(m->mu);  // the index itself is single-threaded
+      int64_t total = 0;
+      for (auto* p : batch) total = std::max(total, p->total);
+      std::vector<eps_filter_node> nodes;
+      if (Prepare(m, head->segment, total, head->n_indexed, head->num_threads) != 0) { rc = EPS_ERR_CUDA; text = eps_last_error(); }
+      if (rc == EPS_OK) {
+        const int lr = LowerFilter(m, head->segment, *head->filter, &nodes, &text);
+        if (lr == -1) { rc = EPS_ERR_CUDA; text = eps_last_error(); }
+        if (lr == -2) { rc = EPS_ERR_UNSUPPORTED; unsupported = true; }
       }
       if (rc == EPS_OK) {
-        for (int64_t i = 0; i < nq; ++i) {
-          batch[i]->count = oc[i];
-          std::memcpy(batch[i]->ids, oi.data() + i * lim, sizeof(int64_t) * lim);
-          std::memcpy(batch[i]->dists, od.data() + i * lim, sizeof(double) * lim);
+        const eps_filter_node* fp = nodes.empty() ? nullptr : nodes.data();
+        if (nq == 1) {  // no copy through staging buffers for a lone request
+          rc = eps_search_batch(m->ix, head->query, 1, static_cast<int64_t>(lim), fp, static_cast<int64_t>(nodes.size()), head->ids, head->dists,
+                                &head->count, nullptr);
+        } else {
+          std::vector<float> qbuf(static_cast<size_t>(nq) * m->dim);
+          for (int64_t i = 0; i < nq; ++i) std::memcpy(qbuf.data() + i * m->dim, batch[i]->query, sizeof(float) * m->dim);
+          std::vector<int64_t> oi(static_cast<size_t>(nq) * lim), oc(static_cast<size_t>(nq));
+          std::vector<double> od(static_cast<size_t>(nq) * lim);
+          rc = eps_search_batch(m->ix, qbuf.data(), nq, static_cast<int64_t>(lim), fp, static_cast<int64_t>(nodes.size()), oi.data(), od.data(),
+                                oc.data(), nullptr);
+          if (rc == EPS_OK) {
+            for (int64_t i = 0; i < nq; ++i) {
+              batch[i]->count = oc[i];
+              std::memcpy(batch[i]->ids, oi.data() + i * lim, sizeof(int64_t) * lim);
+              std::memcpy(batch[i]->dists, od.data() + i * lim, sizeof(double) * lim);
+            }
+          }
         }
+        if (rc != EPS_OK) { text = eps_last_error(); unsupported = rc == EPS_ERR_UNSUPPORTED; }
+        ++m->launches; ++g_launches;
       }
     }
     q.lock();
     m->calls += static_cast<uint64_t>(nq);
     g_calls += nq;
-    for (auto* p : batch) { p->rc = rc; p->err = text; p->done = true; }
+    for (auto* p : batch) { p->rc = rc; p->unsupported = unsupported; p->err = text; p->done = true; }
     m->qcv.notify_all();
   }
   m->leader_active = false;
   m->qcv.notify_all();  // a queued follower (if any) takes over as leader
-  *count = me.count;
-  *err = me.err;
-  return me.rc;
-}
-
-// Device ordinal of the mirrors: EPSILLA_B200_DEVICE (the reference has no GPU setting to read it from).
-static int DeviceOrdinal() {
-  static const int dev = [] { const char* e = std::getenv("EPSILLA_B200_DEVICE"); return e ? std::atoi(e) : 0; }();
-  return dev;
 }
 
 }  // namespace b200
@@ -265,135 +411,25 @@ Status VecSearchExecutor::Search(const VectorPtr query_data, vectordb::engine::T
   b200::Mirror* m = b200::MirrorOf(ann_index_);
   if (m == nullptr || !std::holds_alternative<DenseVectorPtr>(query_data))
     return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: sparse-vector search is out of scope of the GPU path");
-  std::unique_lock<std::mutex> lk(m->mu);
-  const int64_t total = table_segment->record_number_;  // snapshot (:839)
-  if (m->ix == nullptr) {
-    m->capacity = static_cast<int64_t>(table_segment->size_limit_);
-    if (eps_index_create(&m->ix, m->metric, m->dim, m->host_vectors, m->capacity, b200::DeviceOrdinal()) != EPS_OK) return b200::Fail("create");
-    if (eps_index_sync_rows(m->ix, std::max<int64_t>(total, total_indexed_vector_)) != EPS_OK) return b200::Fail("sync_rows");
-    if (total_indexed_vector_ > 0 &&
-        eps_index_set_graph(m->ix, total_indexed_vector_, m->offsets, m->nbrs, m->nav) != EPS_OK)
-      return b200::Fail("set_graph");
-    if (eps_index_config(m->ix, m->L_master, m->L_local, m->prefilter ? 1 : 0, 0) != EPS_OK) return b200::Fail("config");
-    // IntraQueryThreads (config.hpp:18, default 4): 1 = the sequential order, > 1 = that many candidates expanded
-    // concurrently (the reference's parallel mode is itself not a pure function of its inputs)
-    const int width = num_threads_ >= 8 ? 8 : num_threads_ >= 4 ? 4 : num_threads_ >= 2 ? 2 : 1;
-    if (eps_index_set_search_width(m->ix, width) != EPS_OK) return b200::Fail("search_width");
-  }
-  if (eps_index_sync_rows(m->ix, total) != EPS_OK) return b200::Fail("sync_rows");
-  ConcurrentBitset& deleted = *(table_segment->deleted_);  // (:840)
-  if (eps_index_set_deleted(m->ix, deleted.data(), (total + 7) / 8) != EPS_OK) return b200::Fail("set_deleted");
-
-  // filter nodes -> PODs (:841-848): field names resolved through the segment's offset map; string work happens
-  // here, on the host — new rows of the string columns a filter reads are dictionary-encoded and appended to the
-  // device mirror, literals become codes, `x IN (a, b, ..)` becomes `x = a OR x = b ..`.
-  std::vector<eps_filter_node> nodes;
-  {
-    using query::expr::NodeType;
-    using query::expr::ValueType;
-    for (const auto& np : filter_nodes) {
-      if (np->node_type != NodeType::StringAttr) continue;
-      auto it = table_segment->field_name_mem_offset_map_.find(np->field_name);
-      if (it == table_segment->field_name_mem_offset_map_.end()) continue;
-      const size_t col = it->second;
-      if (col >= 8 || col >= table_segment->var_len_attr_table_.size())
-        return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: more than 8 string columns are out of scope of the GPU path");
-      if (m->str_rows.size() <= col) m->str_rows.resize(col + 1, 0);
-      if (m->str_rows[col] < total) {
-        std::vector<int32_t> codes;
-        codes.reserve(static_cast<size_t>(total - m->str_rows[col]));
-        auto& column = table_segment->var_len_attr_table_[col];
-        for (int64_t r = m->str_rows[col]; r < total; ++r) {
-          const std::string* sv = std::get_if<std::string>(&column[r]);
-          auto ins = m->dict.emplace(sv ? *sv : std::string(), static_cast<int32_t>(m->dict.size()));
-          codes.push_back(ins.first->second);
-        }
-        if (eps_index_set_string_codes(m->ix, static_cast<int>(col), m->str_rows[col], codes.data(), static_cast<int64_t>(codes.size())) != EPS_OK)
-          return b200::Fail("set_string_codes");
-        m->str_rows[col] = total;
-      }
-    }
-    std::vector<int64_t> remap(filter_nodes.size(), -1);  // parser index -> index of the POD holding the node's value
-    auto pod = [](NodeType t, ValueType v) {
-      eps_filter_node d;
-      std::memset(&d, 0, sizeof(d));
-      d.node_type = static_cast<int64_t>(t);
-      d.value_type = static_cast<int64_t>(v);
-      d.left = d.right = -1;
-      d.field_offset = -1;
-      return d;
-    };
-    for (size_t i = 0; i < filter_nodes.size(); ++i) {
-      const auto& sn = *filter_nodes[i];
-      if (sn.node_type == NodeType::IN) {  // expr_evaluator.cpp:176-185: last argument is the attribute
-        const size_t len = sn.arguments.size();
-        if (len < 2) return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: malformed IN node");
-        const int64_t attr = remap[sn.arguments[len - 1]];
-        int64_t acc = -1;
-        for (size_t j = 0; j + 1 < len; ++j) {
-          eps_filter_node eq = pod(NodeType::EQ, ValueType::BOOL);
-          eq.left = attr;
-          eq.right = remap[sn.arguments[j]];
-          nodes.push_back(eq);
-          const int64_t eq_at = static_cast<int64_t>(nodes.size()) - 1;
-          if (acc < 0) { acc = eq_at; continue; }
-          eps_filter_node o = pod(NodeType::OR, ValueType::BOOL);
-          o.left = acc;
-          o.right = eq_at;
-          nodes.push_back(o);
-          acc = static_cast<int64_t>(nodes.size()) - 1;
-        }
-        remap[i] = acc;
-        continue;
-      }
-      if (sn.node_type == NodeType::Add && sn.value_type == ValueType::STRING)
-        return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: string concatenation in filters is out of scope of the GPU path");
-      eps_filter_node d = pod(sn.node_type, sn.value_type);
-      const bool unary = sn.node_type == NodeType::NOT;
-      const bool leaf = sn.node_type <= NodeType::GeoPointAttr;
-      if (!leaf) {
-        d.left = sn.left < filter_nodes.size() ? remap[sn.left] : -1;
-        d.right = (!unary && sn.right < filter_nodes.size()) ? remap[sn.right] : -1;
-      }
-      d.int_value = sn.int_value;
-      d.double_value = sn.double_value;
-      d.bool_value = sn.bool_value ? 1 : 0;
-      if (sn.node_type == NodeType::StringConst) {
-        auto it = m->dict.find(sn.str_value);
-        d.int_value = it == m->dict.end() ? -1 : it->second;  // a literal no row carries equals nothing
-      }
-      if (!sn.field_name.empty()) {
-        if (sn.field_name == "@distance") d.field_offset = -2;
-        else {
-          auto it = table_segment->field_name_mem_offset_map_.find(sn.field_name);
-          if (it != table_segment->field_name_mem_offset_map_.end()) d.field_offset = static_cast<int64_t>(it->second);
-        }
-      }
-      nodes.push_back(d);
-      remap[i] = static_cast<int64_t>(nodes.size()) - 1;
-    }
-  }
-  if (!nodes.empty() && (m->attr_rows != total || m->attr_ptr != table_segment->attribute_table_)) {
-    if (eps_index_set_attrs(m->ix, table_segment->attribute_table_, table_segment->primitive_offset_, total) != EPS_OK)
-      return b200::Fail("set_attrs");
-    m->attr_rows = total;
-    m->attr_ptr = table_segment->attribute_table_;
-  }
   if (search_result_.size() < limit) {  // the reference overruns here when limit > L_master
     search_result_.resize(limit);
     distance_.resize(limit);
   }
-  int64_t count = 0;
-  std::string err;
-  // hand the request to the mirror's batch former: release the mirror lock while queued so that the other
-  // executors of the pool (engine/db/execution/executor_pool.hpp) can join the same batch
-  lk.unlock();
-  const int rc = b200::SearchCoalesced(m, std::get<DenseVectorPtr>(query_data), limit, nodes, search_result_.data(), distance_.data(),
-                                       &count, &err);
-  lk.lock();
-  if (rc == EPS_ERR_UNSUPPORTED) return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: " + err);
-  if (rc != EPS_OK) return Status(DB_UNEXPECTED_ERROR, "epsilla_b200: search: " + err);
-  result_size = count;
+  b200::Mirror::Pending me;
+  me.query = std::get<DenseVectorPtr>(query_data);
+  me.limit = limit;
+  me.filter = &filter_nodes;
+  me.key = b200::FilterKey(filter_nodes);
+  me.segment = table_segment;
+  me.total = table_segment->record_number_;  // snapshot (:839)
+  me.n_indexed = total_indexed_vector_;
+  me.num_threads = num_threads_;
+  me.ids = search_result_.data();
+  me.dists = distance_.data();
+  b200::SearchCoalesced(m, &me);
+  if (me.unsupported) return Status(NOT_IMPLEMENTED_ERROR, "epsilla_b200: " + me.err);
+  if (me.rc != EPS_OK) return Status(DB_UNEXPECTED_ERROR, "epsilla_b200: search: " + me.err);
+  result_size = me.count;
   return Status::OK();  // (:934)
 }
 
