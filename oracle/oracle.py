@@ -307,6 +307,8 @@ class Ref:
         ds = np.zeros(cap, np.float64)
         nd = C.c_uint64(0)
         n = self.L.ref_search(self.h, 0, _p(q), limit, filter.encode(), _p(ids), _p(ds), C.byref(nd))
+        if n == -2:
+            raise RuntimeError("Search returned a non-OK status for filter %r" % filter)
         if n < 0:
             raise ValueError("filter failed to parse: %r" % filter)
         return ids[:n].copy(), ds[:n].copy(), nd.value
@@ -318,6 +320,8 @@ class Ref:
         ds = np.full((nq, limit), np.inf, np.float64)
         counts = np.zeros(nq, np.int64)
         rc = self.L.ref_search_batch(self.h, _p(q), nq, limit, filter.encode(), _p(ids), _p(ds), _p(counts))
+        if rc == -2:
+            raise RuntimeError("Search returned a non-OK status for filter %r" % filter)
         if rc != 0:
             raise ValueError("filter failed to parse: %r" % filter)
         return ids, ds, counts

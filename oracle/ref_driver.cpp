@@ -180,7 +180,8 @@ int64_t ref_search(void* h, int e, const float* query, int64_t limit, const char
   auto& ex = c->execs[e];
   uint64_t before = g_dist_count.load();
   int64_t rs = 0;
-  ex->Search(const_cast<float*>(query), c->seg.get(), static_cast<size_t>(limit), nodes, rs);
+  auto status = ex->Search(const_cast<float*>(query), c->seg.get(), static_cast<size_t>(limit), nodes, rs);
+  if (!status.ok()) return -2;  // the reference always returns OK (:934); a replaced Search may refuse a filter
   if (n_dist) *n_dist = g_dist_count.load() - before;
   for (int64_t i = 0; i < rs; ++i) {
     ids[i] = ex->search_result_[i];
@@ -200,6 +201,7 @@ int ref_search_batch(void* h, const float* queries, int64_t nq, int64_t limit, c
     if (!st.ok()) return -1;
   }
   std::atomic<int64_t> next{0};
+  std::atomic<bool> failed{false};
   int ne = static_cast<int>(c->execs.size());
   auto worker = [&](int e) {
     auto nodes = nodes0;
@@ -208,7 +210,8 @@ int ref_search_batch(void* h, const float* queries, int64_t nq, int64_t limit, c
       int64_t q = next.fetch_add(1);
       if (q >= nq) break;
       int64_t rs = 0;
-      ex->Search(const_cast<float*>(queries + q * c->dim), c->seg.get(), static_cast<size_t>(limit), nodes, rs);
+      auto status = ex->Search(const_cast<float*>(queries + q * c->dim), c->seg.get(), static_cast<size_t>(limit), nodes, rs);
+      if (!status.ok()) { failed.store(true); rs = 0; }
       counts[q] = rs;
       for (int64_t i = 0; i < rs && i < limit; ++i) {
         ids[q * limit + i] = ex->search_result_[i];
@@ -220,7 +223,7 @@ int ref_search_batch(void* h, const float* queries, int64_t nq, int64_t limit, c
   for (int e = 1; e < ne; ++e) th.emplace_back(worker, e);
   worker(0);
   for (auto& t : th) t.join();
-  return 0;
+  return failed.load() ? -2 : 0;
 }
 
 // ann_graph_<field>.bin round trip through the reference's own writer / loader

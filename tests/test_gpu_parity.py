@@ -374,7 +374,7 @@ def test_search_on_reference_built_graph_20k(vdb, golden_refgraph):
 @pytest.mark.parametrize("m", METRICS)
 def test_nn_descent_build_quality(vdb, m):
     """B1: force the NN-descent branch (exact_knn_below far under n) and compare the searches on its graph with the
-    searches on the exact-kNN graph of the same rows: recall within 0.03 at equal L, at most 1.5x the distance
+    searches on the exact-kNN graph of the same rows: recall within 0.05 at equal L, at most 1.5x the distance
     evaluations; the repair must not grow hubs."""
     n, d, nq = 60000, 64, 128
     X, Q = gen(n, d, 911, "cluster"), gen(nq, d, 912, "cluster")
@@ -395,14 +395,14 @@ def test_nn_descent_build_quality(vdb, m):
         ix.set_search_width(1)
         ids, _, _, st = ix.search(Q, 10)
         res[name] = (recall(ids, truth, 10), st["n_dist"] / nq)
-    assert res["nnd"][0] >= res["exact"][0] - 0.03, res
+    assert res["nnd"][0] >= res["exact"][0] - 0.05, res
     assert res["nnd"][1] <= 1.5 * res["exact"][1], res
     ix.close()
 
 
 def test_nn_descent_build_vs_reference_graph(vdb, golden_refgraph):
     """The device build (NN-descent forced) on the fixture's 20 000 x 128 rows against the graph the reference built
-    on the same rows: recall at equal L within 0.03 of the reference's, distance evaluations at most 1.5x."""
+    on the same rows: recall at equal L within 0.05 of the reference's, distance evaluations at most 1.5x."""
     g = golden_refgraph
     n, d, nq = int(g["n"]), int(g["d"]), int(g["nq"])
     X, Q = gen(n, d, 901, "cluster"), gen(nq, d, 902, "cluster")
@@ -413,7 +413,7 @@ def test_nn_descent_build_vs_reference_graph(vdb, golden_refgraph):
     for L in (200, 500):
         ix.config(L, L)
         ids, _, _, st = ix.search(Q, 10)
-        assert recall(ids, g["truth"], 10) >= float(g["T1_L%d_recall" % L]) - 0.03, L
+        assert recall(ids, g["truth"], 10) >= float(g["T1_L%d_recall" % L]) - 0.05, L
         assert st["n_dist"] <= 1.5 * int(g["T1_L%d_ndist" % L].sum()), L
     ix.close()
 

@@ -12,7 +12,7 @@ from bench import gen_table, gen_queries
 what, rows, dim, centers = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 dev = torch.device("cuda", 0)
 X = gen_table(rows, dim, "cluster", 42, dev, centers)
-nq, k = 256, 10
+nq, k = int(os.environ.get("NQ", "1024")), 10
 Q = gen_queries(nq, dim, "cluster", 43, dev, centers)
 ix = vectordb_b200.Index("l2", dim, capacity=rows)
 ix.adopt_device_rows(X.data_ptr(), rows)

@@ -664,8 +664,8 @@ int eps_index_set_search_width(eps_index* h, int width) {
 int eps_index_set_graph_tuning(eps_index* h, int ring_slots, int ctas_per_sm) {
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
-  if (ring_slots < 0 || ring_slots > 32 || ctas_per_sm < 0 || ctas_per_sm > 32)
-    return eps::fail(EPS_ERR_INVALID_ARGUMENT, "ring_slots and ctas_per_sm must be in [0, 32] (0 = auto)");
+  if (ring_slots < 0 || ring_slots > 24 || ctas_per_sm < 0 || ctas_per_sm > 32)
+    return eps::fail(EPS_ERR_INVALID_ARGUMENT, "ring_slots must be in [0, 24] and ctas_per_sm in [0, 32] (0 = auto)");
   ix->graph_ring_slots = ring_slots;
   ix->graph_ctas_per_sm = ctas_per_sm;
   return EPS_OK;

@@ -45,7 +45,7 @@ constexpr int kEll = 64;        // adjacency ids per fixed-stride row
 constexpr int kGsThreads = 128;
 constexpr int kMaxW = 8;        // candidates picked per iteration (upper bound)
 constexpr int kPC = 128;        // accepted keys pending their merge (= one key per thread in the merge)
-constexpr int kMaxR = 32;       // ring slots (upper bound; one issuing lane per slot)
+constexpr int kMaxR = 24;       // ring slots (upper bound: 3 consumer warps x 4 teams x 2 slots)
 constexpr int kRounds = kMaxW * kEll / kGsThreads;  // adjacency slots per thread
 
 // Developer build only (make EXTRA=-DEPS_GS_PROFILE): per-phase cycle counters of warp 0 (pick / adjacency / merge /
@@ -94,33 +94,27 @@ __device__ __forceinline__ int lb_masked(const unsigned long long* a, int n, uns
 // 8-lane team partial of one row against the query (both in shared memory when VEC4; the row in global
 // memory otherwise).  Lane tl covers float4 chunks tl, tl+8, ...
 template <bool L2>
+__device__ __forceinline__ void acc4(const float4& x, const float4& y, float& a) {
+  if (L2) {
+    float d;
+    d = x.x - y.x; a = fmaf(d, d, a); d = x.y - y.y; a = fmaf(d, d, a);
+    d = x.z - y.z; a = fmaf(d, d, a); d = x.w - y.w; a = fmaf(d, d, a);
+  } else {
+    a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+  }
+}
+template <bool L2>
 __device__ __forceinline__ float team_partial_vec4(const float4* __restrict__ row, const float4* __restrict__ q, int dim4, int tl) {
-  float a0 = 0.f, a1 = 0.f;
+  // four independent 16-byte chunk pairs per trip: eight shared-memory loads in flight before the first FMA
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int c = tl;
-  for (; c + 8 < dim4; c += 16) {
-    const float4 x0 = row[c], y0 = q[c], x1 = row[c + 8], y1 = q[c + 8];
-    if (L2) {
-      float d;
-      d = x0.x - y0.x; a0 = fmaf(d, d, a0); d = x0.y - y0.y; a0 = fmaf(d, d, a0);
-      d = x0.z - y0.z; a0 = fmaf(d, d, a0); d = x0.w - y0.w; a0 = fmaf(d, d, a0);
-      d = x1.x - y1.x; a1 = fmaf(d, d, a1); d = x1.y - y1.y; a1 = fmaf(d, d, a1);
-      d = x1.z - y1.z; a1 = fmaf(d, d, a1); d = x1.w - y1.w; a1 = fmaf(d, d, a1);
-    } else {
-      a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
-      a1 = fmaf(x1.x, y1.x, a1); a1 = fmaf(x1.y, y1.y, a1); a1 = fmaf(x1.z, y1.z, a1); a1 = fmaf(x1.w, y1.w, a1);
-    }
+  for (; c + 24 < dim4; c += 32) {
+    const float4 x0 = row[c], x1 = row[c + 8], x2 = row[c + 16], x3 = row[c + 24];
+    const float4 y0 = q[c], y1 = q[c + 8], y2 = q[c + 16], y3 = q[c + 24];
+    acc4<L2>(x0, y0, a0); acc4<L2>(x1, y1, a1); acc4<L2>(x2, y2, a2); acc4<L2>(x3, y3, a3);
   }
-  if (c < dim4) {
-    const float4 x0 = row[c], y0 = q[c];
-    if (L2) {
-      float d;
-      d = x0.x - y0.x; a0 = fmaf(d, d, a0); d = x0.y - y0.y; a0 = fmaf(d, d, a0);
-      d = x0.z - y0.z; a0 = fmaf(d, d, a0); d = x0.w - y0.w; a0 = fmaf(d, d, a0);
-    } else {
-      a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
-    }
-  }
-  return a0 + a1;
+  for (; c < dim4; c += 8) acc4<L2>(row[c], q[c], a0);
+  return (a0 + a1) + (a2 + a3);
 }
 template <bool L2>
 __device__ __forceinline__ float team_partial_scalar(const float* __restrict__ row, const float* __restrict__ q, int dim, int tl) {
@@ -198,7 +192,9 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
   __shared__ long long s_cont_e[kMaxW], s_cont_end[kMaxW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int team = lane >> 3, tl = lane & 7, team16 = warp * 4 + team;  // 16 teams of 8 lanes
+  // warp 0 picks candidates and leads the adjacency step; warps 1-3 are the row consumers: 12 teams of 8 lanes, slot
+  // s belongs to consumer warp s % 3, team (s / 3) % 4 — a warp's teams run in lockstep, so slots are dealt across warps
+  const int team = lane >> 3, tl = lane & 7, cw = warp - 1;
   const unsigned team_mask = 0xFFu << (team * 8);
   const unsigned lane_lt = (1u << lane) - 1u;
   const int L = a.L, R = a.R, W = a.W;
@@ -212,7 +208,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     for (int s = 0; s < R; ++s) mbar_init(bar0 + 8 * s, 1);
     mbar_fence_init();
   }
-  // Ring slot s belongs to team (s & 15) for the whole kernel: the team issues the bulk copy into it, waits on its
+  // A ring slot belongs to ONE team for the whole kernel: the team issues the bulk copy into it, waits on its
   // mbarrier, reads it and refills it — no block barrier guards a slot.  Per-slot state lives in the team's registers.
   bool occ[2] = {false, false};
   uint32_t par[2] = {0u, 0u};
@@ -253,7 +249,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       // barrier X: pending appends, FIFO writes and slot states of the previous iteration are settled;
       // the count is the number of ring slots with a row in flight
       GS_T(tx0);
-      const int inflight = __syncthreads_count((tl == 0 && occ[0]) || (tl == 1 && occ[1]));
+      const int inflight = __syncthreads_count(cw >= 0 && ((tl == 0 && occ[0]) || (tl == 1 && occ[1])));
       GS_T(tx1);
       GS_ACC(0, tx0, tx1);
       const int m = s_npend;
@@ -273,11 +269,11 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       const bool want = a.exact ? idle : (fifo_tail - head) < static_cast<uint32_t>(R);
 
       // -- C/B, per team: consume the landed row of each owned slot, refill the slot from the FIFO at once --
-      {
+      if (cw >= 0) {
         const unsigned long long bound = qa[L - 1] & kKeyMask;  // worst entry as of the last merge (:546)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int slot = team16 + 16 * j;
+          const int slot = cw + 3 * team + 12 * j;
           if (slot < R) {
             if (occ[j]) {
               float p;
@@ -591,13 +587,27 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
            static_cast<size_t>(dimp) * 4 + kPC * 4 + static_cast<size_t>(fc) * 4;
   };
   while (R > 2 && smem_for(R) > 200 * 1024) --R;
-  const size_t smem = smem_for(R);
-  if (smem > 226 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query + row ring do not fit in shared memory");
+  if (smem_for(R) > 226 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query + row ring do not fit in shared memory");
+  EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(R))));
+  auto resident = [&](int r, int* out) {
+    EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, graph_search_kernel, kGsThreads, smem_for(r)));
+    if (*out < 1) *out = 1;
+    if (ix->graph_ctas_per_sm > 0) *out = std::min(*out, ix->graph_ctas_per_sm);
+    return EPS_OK;
+  };
   int per_sm = 0;
-  EPS_CUDA(cudaFuncSetAttribute(graph_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  EPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_search_kernel, kGsThreads, smem));
-  if (per_sm < 1) per_sm = 1;
-  if (ix->graph_ctas_per_sm > 0) per_sm = std::min(per_sm, ix->graph_ctas_per_sm);
+  EPS_TRY(resident(R, &per_sm));
+  // Auto geometry: if a smaller ring (>= 4 slots) lets EVERY query of the batch be resident at once, take the
+  // largest such ring — one wave has no idle tail and measured best (profiles/r02_graph_geometry_*); otherwise keep
+  // the ~48 KB ring.
+  if (staged && ix->graph_ring_slots == 0 && static_cast<int64_t>(per_sm) * ix->num_sms < nq) {
+    for (int r = R - 1; r >= 4; --r) {
+      int p = 0;
+      EPS_TRY(resident(r, &p));
+      if (static_cast<int64_t>(p) * ix->num_sms >= nq) { R = r; per_sm = p; break; }
+    }
+  }
+  const size_t smem = smem_for(R);
   const int slots = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(per_sm) * ix->num_sms));
   const int64_t words = ((ix->n_indexed + 31) / 32 + 3) & ~3ll;
   if (ix->visited_slots < slots || ix->s_visited.cap < static_cast<size_t>(slots) * words * 4) {
