@@ -33,6 +33,7 @@
 // wide mode (width W = 2/4/8): up to W candidates are picked per iteration from queue ∪ pending while the rows
 //   of the previous iteration are still in flight — the device analogue of IntraQueryThreads > 1; like that
 //   mode it is not bit-identical to the sequential order.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -79,6 +80,7 @@ struct GSArgs {
   int exact;
   int R;                          // ring slots (slot s is owned by 8-lane team s & 15)
   int fc;                         // fresh-id FIFO capacity (power of two)
+  unsigned long long* qtimes;     // developer build: [nq x 2] globaltimer at query start / end (null otherwise)
   int slot_bytes;                 // ring slot pitch (row bytes, multiple of 16); 0 when rows are not staged
 };
 
@@ -225,6 +227,9 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     __syncthreads();
     const int q = s_q;
     if (q >= a.nq) break;
+#ifdef EPS_GS_PROFILE
+    if (tid == 0 && a.qtimes) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.qtimes[2 * q] = t; }
+#endif
 
     // ---- seed (InitializeSetLPara): precomputed distances of the query-independent seed set ----
     for (int i = tid; i < a.dim; i += kGsThreads) qv[i] = a.queries[static_cast<int64_t>(q) * a.dim + i];
@@ -475,6 +480,9 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     }
     unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
     for (int i = tid; i < L; i += kGsThreads) out[i] = qa[i];
+#ifdef EPS_GS_PROFILE
+    if (tid == 0 && a.qtimes) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.qtimes[2 * q + 1] = t; }
+#endif
     {
       uint4* v4 = reinterpret_cast<uint4*>(visited);
       const int64_t n4 = a.visited_words >> 2;
@@ -655,6 +663,12 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   a.visited_words = words; a.seed_ld = seed_ld; a.dim = dim; a.metric = ix->metric;
   a.vec4 = ix->vec4 ? 1 : 0; a.L = static_cast<int>(L); a.Lp = Lp; a.nq = static_cast<int>(nq);
   a.W = width; a.exact = width == 1 ? 1 : 0; a.R = R; a.slot_bytes = slot_bytes; a.fc = fc;
+  a.qtimes = nullptr;
+#ifdef EPS_GS_PROFILE
+  EPS_TRY(ix->s_tail.reserve(static_cast<size_t>(nq) * 16));  // borrowed scratch (the hybrid tail buffer is filled after the search)
+  a.qtimes = ix->s_tail.as<unsigned long long>();
+  ix->prof_nq = nq;
+#endif
   graph_search_kernel<<<slots, kGsThreads, smem, ix->stream>>>(a);
   EPS_CUDA(cudaGetLastError());
   if (stats) {
@@ -681,6 +695,19 @@ int read_graph_counters(Index* ix, eps_stats* stats) {
   for (int w = 0; w < 2; ++w)
     for (int i = 0; i < 8; ++i) fprintf(stderr, " w%d.%s=%.1f%%", w, names[i], 100.0 * static_cast<double>(pr[8 + w * 8 + i]) / tot);
   fprintf(stderr, "\n");
+  if (ix->prof_nq > 0 && ix->s_tail.p) {
+    std::vector<unsigned long long> t(static_cast<size_t>(ix->prof_nq) * 2);
+    EPS_CUDA(cudaMemcpy(t.data(), ix->s_tail.p, t.size() * 8, cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for (int64_t q = 0; q < ix->prof_nq; ++q) { t0 = std::min(t0, t[2 * q]); t1 = std::max(t1, t[2 * q + 1]); }
+    std::vector<double> end, dur;
+    for (int64_t q = 0; q < ix->prof_nq; ++q) { end.push_back((t[2 * q + 1] - t0) * 1e-3); dur.push_back((t[2 * q + 1] - t[2 * q]) * 1e-3); }
+    std::sort(end.begin(), end.end());
+    std::sort(dur.begin(), dur.end());
+    const size_t n = end.size();
+    fprintf(stderr, "[gs-profile] span %.0f us; query END times (us) p10 %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f; query DURATION (us) p10 %.0f p50 %.0f p90 %.0f max %.0f\n",
+            (t1 - t0) * 1e-3, end[n / 10], end[n / 2], end[n * 9 / 10], end[n * 99 / 100], end[n - 1], dur[n / 10], dur[n / 2], dur[n * 9 / 10], dur[n - 1]);
+  }
 #endif
   return EPS_OK;
 }

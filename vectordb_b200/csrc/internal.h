@@ -92,6 +92,7 @@ struct Index {
   int64_t vis_clean_words = 0;
   size_t vis_clean_cap = 0;
   bool graph_counters_pending = false;
+  int64_t prof_nq = 0;           // developer build (EPS_GS_PROFILE): queries of the last profiled launch
   void* h_out = nullptr;         // pinned host mirror of the packed result block (eps_search_batch)
   size_t h_out_cap = 0;
 };
