@@ -46,7 +46,8 @@ constexpr int kEll = 64;        // adjacency ids per fixed-stride row
 constexpr int kGsThreads = 128;
 constexpr int kMaxW = 8;        // candidates picked per iteration (upper bound)
 constexpr int kPC = 128;        // accepted keys pending their merge (= one key per thread in the merge)
-constexpr int kMaxR = 24;       // ring slots (upper bound: 3 consumer warps x 4 teams x 2 slots)
+constexpr int kMaxS = 8;        // ring slots per consumer warp (upper bound)
+constexpr int kMaxR = 24;       // ring slots (upper bound: 3 consumer warps x kMaxS)
 constexpr int kRounds = kMaxW * kEll / kGsThreads;  // adjacency slots per thread
 
 // Developer build only (make EXTRA=-DEPS_GS_PROFILE): per-phase cycle counters of warp 0 (pick / adjacency / merge /
@@ -78,7 +79,7 @@ struct GSArgs {
   int nq;
   int W;                          // candidates per iteration (1 in exact mode)
   int exact;
-  int R;                          // ring slots (slot s is owned by 8-lane team s & 15)
+  int R;                          // ring slots (slot s is owned by consumer warp s % 3)
   int fc;                         // fresh-id FIFO capacity (power of two)
   unsigned long long* qtimes;     // developer build: [nq x 2] globaltimer at query start / end (null otherwise)
   int slot_bytes;                 // ring slot pitch (row bytes, multiple of 16); 0 when rows are not staged
@@ -93,8 +94,6 @@ __device__ __forceinline__ int lb_masked(const unsigned long long* a, int n, uns
   return lo;
 }
 
-// 8-lane team partial of one row against the query (both in shared memory when VEC4; the row in global
-// memory otherwise).  Lane tl covers float4 chunks tl, tl+8, ...
 template <bool L2>
 __device__ __forceinline__ void acc4(const float4& x, const float4& y, float& a) {
   if (L2) {
@@ -105,27 +104,75 @@ __device__ __forceinline__ void acc4(const float4& x, const float4& y, float& a)
     a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
   }
 }
-template <bool L2>
-__device__ __forceinline__ float team_partial_vec4(const float4* __restrict__ row, const float4* __restrict__ q, int dim4, int tl) {
-  // four independent 16-byte chunk pairs per trip: eight shared-memory loads in flight before the first FMA
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int c = tl;
-  for (; c + 24 < dim4; c += 32) {
-    const float4 x0 = row[c], x1 = row[c + 8], x2 = row[c + 16], x3 = row[c + 24];
-    const float4 y0 = q[c], y1 = q[c + 8], y2 = q[c + 16], y3 = q[c + 24];
-    acc4<L2>(x0, y0, a0); acc4<L2>(x1, y1, a1); acc4<L2>(x2, y2, a2); acc4<L2>(x3, y3, a3);
+// Distances of up to S landed rows (ring slots of ONE consumer warp) to the query, all 32 lanes on every row: lane l
+// covers float4 chunks l, l + 32, ...; a query chunk is loaded once per trip and used against all S rows, so shared-
+// memory traffic per row is (1 + 1/S) chunks instead of 2.  `mask` bit s = row s is occupied; row s lives at first + s * step.
+template <bool L2, int S>
+__device__ __forceinline__ void warp_rows_vec4(const unsigned char* first, uint32_t step, unsigned mask, const float4* __restrict__ q,
+                                               int dim4, int lane, float (&out)[S]) {
+  float acc[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) acc[s] = 0.f;
+  for (int c = lane; c < dim4; c += 32) {
+    const float4 y = q[c];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      if ((mask >> s) & 1u) acc4<L2>(reinterpret_cast<const float4*>(first + s * step)[c], y, acc[s]);
   }
-  for (; c < dim4; c += 8) acc4<L2>(row[c], q[c], a0);
-  return (a0 + a1) + (a2 + a3);
+#pragma unroll
+  for (int s = 0; s < S; ++s) out[s] = warp_sum(acc[s]);
 }
-template <bool L2>
-__device__ __forceinline__ float team_partial_scalar(const float* __restrict__ row, const float* __restrict__ q, int dim, int tl) {
-  float a = 0.f;
-  for (int i = tl; i < dim; i += 8) {
-    const float x = __ldg(row + i), y = q[i];
-    if (L2) { const float d = x - y; a = fmaf(d, d, a); } else { a = fmaf(x, y, a); }
+// rows not staged (dim % 4 != 0 or a misaligned table): lanes stride the scalars of the global rows
+template <bool L2, int S>
+__device__ __forceinline__ void warp_rows_scalar(const float* const (&rows)[S], unsigned mask, const float* __restrict__ q, int dim,
+                                                 int lane, float (&out)[S]) {
+  float acc[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) acc[s] = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    const float y = q[i];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if ((mask >> s) & 1u) {
+        const float x = __ldg(rows[s] + i);
+        if (L2) { const float d = x - y; acc[s] = fmaf(d, d, acc[s]); } else { acc[s] = fmaf(x, y, acc[s]); }
+      }
+    }
   }
-  return a;
+#pragma unroll
+  for (int s = 0; s < S; ++s) out[s] = warp_sum(acc[s]);
+}
+
+// Consumer step of one warp over its S slots (slot of local index s = cw + 3 s): wait for the landed rows, distances,
+// accepted keys to the pending buffer.  Returns nothing; the caller refills the slots.
+template <int S>
+__device__ __forceinline__ void consume_slots(const GSArgs& a, unsigned occ_mask, unsigned par_mask, int cw, int lane, bool staged,
+                                              const unsigned char* ring, uint32_t bar0, const float* qv, const int* slot_id,
+                                              unsigned long long bound, unsigned long long* pend, int* s_npend) {
+  float d[S];
+  if (staged) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      if ((occ_mask >> s) & 1u) mbar_wait(bar0 + 8 * (cw + 3 * s), (par_mask >> s) & 1u);
+    const unsigned char* first = ring + static_cast<size_t>(cw) * a.slot_bytes;
+    const uint32_t step = 3u * static_cast<uint32_t>(a.slot_bytes);
+    if (a.metric == EPS_METRIC_L2) warp_rows_vec4<true, S>(first, step, occ_mask, reinterpret_cast<const float4*>(qv), a.dim >> 2, lane, d);
+    else warp_rows_vec4<false, S>(first, step, occ_mask, reinterpret_cast<const float4*>(qv), a.dim >> 2, lane, d);
+  } else {
+    const float* rows[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) rows[s] = a.vectors + static_cast<int64_t>(((occ_mask >> s) & 1u) ? slot_id[cw + 3 * s] : 0) * a.dim;
+    if (a.metric == EPS_METRIC_L2) warp_rows_scalar<true, S>(rows, occ_mask, qv, a.dim, lane, d);
+    else warp_rows_scalar<false, S>(rows, occ_mask, qv, a.dim, lane, d);
+  }
+  // lane s publishes row s
+  float mine = 0.f;
+#pragma unroll
+  for (int s = 0; s < S; ++s) if (lane == s) mine = d[s];
+  if (lane < S && ((occ_mask >> lane) & 1u)) {
+    const unsigned long long key = make_key(finish_metric(a.metric, mine), static_cast<uint32_t>(slot_id[cw + 3 * lane]));
+    if (key < bound) pend[atomicAdd(s_npend, 1)] = key;  // dist > bound rejected (:424); ties by id
+  }
 }
 
 // Block-wide merge of the m (<= kPC) pending keys into the sorted queue qa[0..L): sort by counting, binary-search
@@ -187,6 +234,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
   float* qv = reinterpret_cast<float*>(bars + kMaxR);                                              // [dim4p]
   int* pos = reinterpret_cast<int*>(qv + dim4p);                                                   // [kPC]
   int* fifo = pos + kPC;                                                                           // [fc]
+  int* slot_id = fifo + a.fc;                                                                      // [kMaxR] row id in each ring slot
   __shared__ int s_q, s_ncur, s_cursor, s_npend, s_ncont;
   __shared__ unsigned s_head;                      // FIFO entries [s_head, fifo_tail) are not yet issued to the ring
   __shared__ int s_cid[kMaxW];
@@ -194,10 +242,9 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
   __shared__ long long s_cont_e[kMaxW], s_cont_end[kMaxW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // warp 0 picks candidates and leads the adjacency step; warps 1-3 are the row consumers: 12 teams of 8 lanes, slot
-  // s belongs to consumer warp s % 3, team (s / 3) % 4 — a warp's teams run in lockstep, so slots are dealt across warps
-  const int team = lane >> 3, tl = lane & 7, cw = warp - 1;
-  const unsigned team_mask = 0xFFu << (team * 8);
+  // warp 0 picks candidates and leads the adjacency step; warps 1-3 are the row consumers: ring slot s belongs to
+  // consumer warp s % 3 for the whole kernel (local index s / 3, at most kMaxS per warp)
+  const int cw = warp - 1;
   const unsigned lane_lt = (1u << lane) - 1u;
   const int L = a.L, R = a.R, W = a.W;
   const unsigned fmask = static_cast<unsigned>(a.fc) - 1u;
@@ -210,11 +257,10 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     for (int s = 0; s < R; ++s) mbar_init(bar0 + 8 * s, 1);
     mbar_fence_init();
   }
-  // A ring slot belongs to ONE team for the whole kernel: the team issues the bulk copy into it, waits on its
-  // mbarrier, reads it and refills it — no block barrier guards a slot.  Per-slot state lives in the team's registers.
-  bool occ[2] = {false, false};
-  uint32_t par[2] = {0u, 0u};
-  int sid[2] = {0, 0};
+  // The owning warp issues the bulk copy into a slot, waits on its mbarrier, reads it and refills it — no block
+  // barrier guards a slot.  Per-slot state (occupied, mbarrier phase parity) is a pair of warp-uniform bit masks.
+  unsigned occ_mask = 0u, par_mask = 0u;
+  const int n_own = cw >= 0 ? (R - cw + 2) / 3 : 0;  // slots cw, cw + 3, ... < R
   unsigned long long st_ndist = 0, st_nexp = 0, st_nedge = 0;
 #ifdef EPS_GS_PROFILE
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 0 barrier X, 1 merge, 2 row wait, 3 row math, 4 pick, 5 barrier 1, 6 adjacency+visited, 7 barrier 2 + FIFO
@@ -254,7 +300,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       // barrier X: pending appends, FIFO writes and slot states of the previous iteration are settled;
       // the count is the number of ring slots with a row in flight
       GS_T(tx0);
-      const int inflight = __syncthreads_count(cw >= 0 && ((tl == 0 && occ[0]) || (tl == 1 && occ[1])));
+      const int inflight = __syncthreads_count(lane < kMaxS && ((occ_mask >> lane) & 1u));
       GS_T(tx1);
       GS_ACC(0, tx0, tx1);
       const int m = s_npend;
@@ -273,57 +319,37 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       // has been consumed and merged (exact)
       const bool want = a.exact ? idle : (fifo_tail - head) < static_cast<uint32_t>(R);
 
-      // -- C/B, per team: consume the landed row of each owned slot, refill the slot from the FIFO at once --
-      if (cw >= 0) {
+      // -- C/B, per consumer warp: distances of the landed rows of its slots, then refill every slot from the FIFO --
+      if (n_own > 0) {
         const unsigned long long bound = qa[L - 1] & kKeyMask;  // worst entry as of the last merge (:546)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int slot = cw + 3 * team + 12 * j;
-          if (slot < R) {
-            if (occ[j]) {
-              float p;
-              if (staged) {
-                GS_T(tw0);
-                mbar_wait(bar0 + 8 * slot, par[j]);
-                GS_T(tw1);
-                GS_ACC(2, tw0, tw1);
-                par[j] ^= 1u;
-                const float4* row = reinterpret_cast<const float4*>(ring + static_cast<size_t>(slot) * a.slot_bytes);
-                p = a.metric == EPS_METRIC_L2 ? team_partial_vec4<true>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl)
-                                              : team_partial_vec4<false>(row, reinterpret_cast<const float4*>(qv), a.dim >> 2, tl);
-              } else {
-                const float* row = a.vectors + static_cast<int64_t>(sid[j]) * a.dim;
-                p = a.metric == EPS_METRIC_L2 ? team_partial_scalar<true>(row, qv, a.dim, tl) : team_partial_scalar<false>(row, qv, a.dim, tl);
-              }
-              p += __shfl_xor_sync(team_mask, p, 4);
-              p += __shfl_xor_sync(team_mask, p, 2);
-              p += __shfl_xor_sync(team_mask, p, 1);  // every lane of the team has finished reading the slot
-              if (tl == 0) {
-                const unsigned long long key = make_key(finish_metric(a.metric, p), static_cast<uint32_t>(sid[j]));
-                if (key < bound) pend[atomicAdd(&s_npend, 1)] = key;  // dist > bound rejected (:424); ties by id
-              }
-              occ[j] = false;
-            }
-            GS_T(tc1);
-            GS_ACC(3, tm1, tc1);  // team phase so far (row wait included; subtract slot 2)
-            unsigned idx = 0;
-            if (tl == 0) {
-              idx = atomicAdd(&s_head, 1u);
-              if (idx >= fifo_tail) atomicSub(&s_head, 1u);  // nothing left: hand the index back
-            }
-            idx = __shfl_sync(team_mask, idx, team * 8);
-            if (idx < fifo_tail) {
-              sid[j] = fifo[idx & fmask];
-              occ[j] = true;
-              if (staged && tl == 0) {
-                const uint32_t bar = bar0 + 8 * slot;
-                mbar_expect_tx(bar, row_bytes);
-                bulk_load_1d(ring0 + slot * static_cast<uint32_t>(a.slot_bytes), a.vectors + static_cast<int64_t>(sid[j]) * a.dim,
-                             row_bytes, bar);
-              }
+        if (occ_mask) {
+          GS_T(tw0);
+          if (n_own <= 1) consume_slots<1>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
+          else if (n_own <= 2) consume_slots<2>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
+          else if (n_own <= 4) consume_slots<4>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
+          else consume_slots<8>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
+          par_mask ^= occ_mask;
+          GS_T(tw1);
+          GS_ACC(3, tw0, tw1);
+        }
+        __syncwarp();  // every lane has finished reading the slots
+        bool got = false;
+        if (lane < n_own) {
+          const unsigned idx = atomicAdd(&s_head, 1u);
+          if (idx >= fifo_tail) atomicSub(&s_head, 1u);  // nothing left: hand the index back
+          else {
+            const int slot = cw + 3 * lane;
+            const int id = fifo[idx & fmask];
+            slot_id[slot] = id;
+            got = true;
+            if (staged) {
+              const uint32_t bar = bar0 + 8 * slot;
+              mbar_expect_tx(bar, row_bytes);
+              bulk_load_1d(ring0 + slot * static_cast<uint32_t>(a.slot_bytes), a.vectors + static_cast<int64_t>(id) * a.dim, row_bytes, bar);
             }
           }
         }
+        occ_mask = __ballot_sync(kFull, got);
       }
       if (!want) continue;
       GS_T(tp0);
@@ -592,7 +618,7 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   const int fc = next_pow2(std::max(width * kEll, kGsThreads) + kMaxR);
   auto smem_for = [&](int r) {
     return static_cast<size_t>(r) * slot_bytes + static_cast<size_t>(Lp) * 8 + 2 * kPC * 8 + kMaxR * 8 +
-           static_cast<size_t>(dimp) * 4 + kPC * 4 + static_cast<size_t>(fc) * 4;
+           static_cast<size_t>(dimp) * 4 + kPC * 4 + static_cast<size_t>(fc) * 4 + kMaxR * 4;
   };
   while (R > 2 && smem_for(R) > 200 * 1024) --R;
   if (smem_for(R) > 226 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query + row ring do not fit in shared memory");
