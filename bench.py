@@ -65,7 +65,7 @@ def parse():
     p.add_argument("--centers", type=int, default=1024)
     p.add_argument("--modes", default="graph,brute-bf16", help="candidate modes: graph, brute-bf16, brute-tf32, brute-fp32")
     p.add_argument("--L-sweep", default="256,512,1024,2048,4096", help="graph queue lengths, ascending; stops at the first that reaches the recall target")
-    p.add_argument("--width", type=int, default=8, help="graph search width (1 = the reference's sequential order)")
+    p.add_argument("--width", type=int, default=6, help="graph search width (1 = the reference's sequential order)")
     p.add_argument("--ring", type=int, default=0, help="graph kernel: TMA row-ring slots per CTA (0 = auto)")
     p.add_argument("--ctas", type=int, default=0, help="graph kernel: resident CTAs per SM (0 = auto)")
     p.add_argument("--knn-k", type=int, default=64)
