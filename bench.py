@@ -64,7 +64,7 @@ def parse():
     p.add_argument("--dist", default="cluster", choices=["uniform", "cluster"])
     p.add_argument("--centers", type=int, default=1024)
     p.add_argument("--modes", default="graph,brute-bf16", help="candidate modes: graph, brute-bf16, brute-tf32, brute-fp32")
-    p.add_argument("--L-sweep", default="256,512,1024,2048,4096", help="graph queue lengths, ascending; stops at the first that reaches the recall target")
+    p.add_argument("--L-sweep", default="256,512,1024,1536,2048,3072,4096", help="graph queue lengths, ascending; stops at the first that reaches the recall target")
     p.add_argument("--width", type=int, default=6, help="graph search width (1 = the reference's sequential order)")
     p.add_argument("--ring", type=int, default=0, help="graph kernel: TMA row-ring slots per CTA (0 = auto)")
     p.add_argument("--ctas", type=int, default=0, help="graph kernel: resident CTAs per SM (0 = auto)")
@@ -397,6 +397,7 @@ class Arena:
         self.out_d = torch.empty((a.batch, a.k), dtype=torch.float32, device=dev)
         self.out_c = torch.empty((a.batch,), dtype=torch.int64, device=dev)
         self.stream = torch.cuda.ExternalStream(self.ix.stream, device=dev)
+        torch.cuda.synchronize()  # the library launches on its own non-blocking stream: the generators must be done
 
     def search(self, q, **kw):
         return self.ix.search_device(q.data_ptr(), self.a.batch, self.a.k, self.out_ids.data_ptr(), self.out_d.data_ptr(),

@@ -34,7 +34,7 @@ P.add_argument("--centers", type=int, default=1024)
 P.add_argument("--width", type=int, default=8)
 P.add_argument("--ring", type=int, default=0)
 P.add_argument("--ctas", type=int, default=0)
-P.add_argument("--L-sweep", default="256,512,1024,2048,4096")
+P.add_argument("--L-sweep", default="256,512,1024,1536,2048,3072,4096")
 P.add_argument("--no-cpu", action="store_true")
 P.add_argument("--cpu-timeout", type=int, default=600)
 A = P.parse_args()
@@ -86,6 +86,7 @@ def graph_config(name, rows, dim, metric, nq, k, filt=None, local=0, rank=0, wor
         Q /= Q.norm(dim=1, keepdim=True)
     ix = vectordb_b200.Index(metric, dim, capacity=rows, device=local)
     ix.adopt_device_rows(X.data_ptr(), rows)
+    torch.cuda.synchronize()  # generators done before the library stream reads
     nodes = None
     if filt:
         attr = (np.arange(rows) % filt[2]).astype(np.int32)

@@ -18,6 +18,7 @@ X = gen_table(rows, dim, dist, 42, dev, centers)
 Q = gen_queries(nq, dim, dist, 43, dev, centers)
 ix = vectordb_b200.Index("l2", dim, capacity=rows)
 ix.adopt_device_rows(X.data_ptr(), rows)
+torch.cuda.synchronize()  # generators done before the library stream reads
 oi = torch.empty((nq, k), dtype=torch.int64, device=dev); od = torch.empty((nq, k), dtype=torch.float32, device=dev)
 oc = torch.empty((nq,), dtype=torch.int64, device=dev)
 ix.config(512, 512, force_brute=True)

@@ -16,6 +16,7 @@ nq, k = int(os.environ.get("NQ", "1024")), 10
 Q = gen_queries(nq, dim, "cluster", 43, dev, centers)
 ix = vectordb_b200.Index("l2", dim, capacity=rows)
 ix.adopt_device_rows(X.data_ptr(), rows)
+torch.cuda.synchronize()  # generators done before the library stream reads
 path = "/tmp/repro_graph_%d_%d_%d.npz" % (rows, dim, centers)
 if what == "build":
     t0 = time.perf_counter()

@@ -631,18 +631,24 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   };
   int per_sm = 0;
   EPS_TRY(resident(R, &per_sm));
-  // Auto geometry: if a smaller ring (>= 4 slots) lets EVERY query of the batch be resident at once, take the
-  // largest such ring — one wave has no idle tail and measured best (profiles/r02_graph_geometry_*); otherwise keep
-  // the ~48 KB ring.
-  if (staged && ix->graph_ring_slots == 0 && static_cast<int64_t>(per_sm) * ix->num_sms < nq) {
+  // Auto geometry.  A batch of nq queries runs in rounds = ceil(nq / resident CTAs) waves of whole queries, and a
+  // partly filled last wave is pure loss while the kernel is latency-bound; so among ring sizes >= 4 take the one
+  // with the fewest rounds (a smaller ring = more resident queries), the largest ring on ties, and launch exactly
+  // ceil(nq / rounds) CTAs so that every CTA serves the same number of queries (profiles/r02_graph_geometry_*).
+  auto rounds_of = [&](int p) { return (nq + static_cast<int64_t>(p) * ix->num_sms - 1) / (static_cast<int64_t>(p) * ix->num_sms); };
+  if (staged && ix->graph_ring_slots == 0 && rounds_of(per_sm) > 1) {
+    int best_r = R, best_p = per_sm;
     for (int r = R - 1; r >= 4; --r) {
       int p = 0;
       EPS_TRY(resident(r, &p));
-      if (static_cast<int64_t>(p) * ix->num_sms >= nq) { R = r; per_sm = p; break; }
+      if (rounds_of(p) < rounds_of(best_p)) { best_r = r; best_p = p; }
     }
+    R = best_r;
+    per_sm = best_p;
   }
   const size_t smem = smem_for(R);
-  const int slots = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(per_sm) * ix->num_sms));
+  const int64_t rounds = rounds_of(per_sm);
+  const int slots = static_cast<int>(std::min<int64_t>((nq + rounds - 1) / rounds, static_cast<int64_t>(per_sm) * ix->num_sms));
   const int64_t words = ((ix->n_indexed + 31) / 32 + 3) & ~3ll;
   if (ix->visited_slots < slots || ix->s_visited.cap < static_cast<size_t>(slots) * words * 4) {
     EPS_TRY(ix->s_visited.reserve(static_cast<size_t>(slots) * words * 4));
