@@ -180,7 +180,7 @@ __device__ __forceinline__ void consume_slots(const GSArgs& a, unsigned occ_mask
 // number of pending keys that precede it), drop the keys into the holes.  Entries pushed past L are evicted
 // (AddIntoQueue's drop-worst, :104-108).  Returns the lowest insert position through *s_cursor (min).
 __device__ __forceinline__ void merge_pending(unsigned long long* qa, unsigned long long* pend, unsigned long long* cs, int* pos,
-                                              int m, int L, int* s_npend, int* s_cursor) {
+                                              int m, int L, int* s_npend, int* s_cursor, unsigned* ubits) {
   const int tid = threadIdx.x;
   if (tid < m) {
     const unsigned long long key = pend[tid];
@@ -221,6 +221,16 @@ __device__ __forceinline__ void merge_pending(unsigned long long* qa, unsigned l
     if (p0 < *s_cursor) *s_cursor = p0;
   }
   __syncthreads();
+  // the unchecked-entry bitmap (one bit per queue slot, what the pick scans) from the first changed word on
+  if (p0 < L) {
+    const int nwords = (L + 31) >> 5, lane = tid & 31;
+    for (int w = (p0 >> 5) + (tid >> 5); w < nwords; w += kGsThreads / 32) {
+      const int idx = w * 32 + lane;
+      const unsigned b = __ballot_sync(kFull, idx < L && !(qa[idx] & kCheckedBit));
+      if (lane == 0) ubits[w] = b;
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
@@ -235,6 +245,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
   int* pos = reinterpret_cast<int*>(qv + dim4p);                                                   // [kPC]
   int* fifo = pos + kPC;                                                                           // [fc]
   int* slot_id = fifo + a.fc;                                                                      // [kMaxR] row id in each ring slot
+  unsigned* ubits = reinterpret_cast<unsigned*>(slot_id + kMaxR);                                  // [(Lp + 31) / 32] unchecked-entry bitmap
   __shared__ int s_q, s_ncur, s_cursor, s_npend, s_ncont;
   __shared__ unsigned s_head;                      // FIFO entries [s_head, fifo_tail) are not yet issued to the ring
   __shared__ int s_cid[kMaxW];
@@ -292,6 +303,8 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     if (tid == 0) { s_npend = 0; s_ncont = 0; s_cursor = 0; s_ncur = 0; s_head = 0u; }
     __syncthreads();
     block_bitonic_sort(qa, a.Lp);
+    for (int w = tid; w < ((L + 31) >> 5); w += kGsThreads)  // every seed starts unchecked
+      ubits[w] = (w * 32 + 32 <= L) ? 0xffffffffu : ((1u << (L & 31)) - 1u);
     if (tid == 0) st_ndist += static_cast<unsigned long long>(L);
     uint32_t fifo_tail = 0;
 
@@ -310,7 +323,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       const bool merged = m > 0 && (a.exact || m > kPC - R);
       // s_npend / s_head are bumped by the team phase below: no thread may get there before EVERY thread has taken
       // the snapshot above (the merge's own barriers do that when there is a merge)
-      if (merged) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor);
+      if (merged) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor, ubits);
       else __syncthreads();
       GS_T(tm1);
       GS_ACC(1, tx1, tm1);
@@ -371,11 +384,20 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
           bool pscan = np > 0;
           while (cnt < W) {
             int qpos = -1;
-            for (int p = sp; p < L; p += 32) {
-              const int idx = p + lane;
-              const bool un = idx < L && !(qa[idx] & kCheckedBit);
-              const unsigned b = __ballot_sync(kFull, un);
-              if (b) { qpos = p + __ffs(b) - 1; break; }
+            {
+              const int nwords = (L + 31) >> 5;
+              for (int w0 = sp >> 5; w0 < nwords; w0 += 32) {
+                const int wi = w0 + lane;
+                unsigned word = wi < nwords ? ubits[wi] : 0u;
+                if (wi == (sp >> 5)) word &= ~((1u << (sp & 31)) - 1u);  // entries before the cursor are checked
+                const unsigned b = __ballot_sync(kFull, word != 0u);
+                if (b) {
+                  const int src = __ffs(b) - 1;
+                  const unsigned wsel = __shfl_sync(kFull, word, src);
+                  qpos = (w0 + src) * 32 + __ffs(wsel) - 1;
+                  break;
+                }
+              }
             }
             if (qpos < 0) sp = L;  // queue exhausted: later picks of this iteration do not rescan it
             const unsigned long long qkey = qpos >= 0 ? (qa[qpos] & kKeyMask) : ~0ull;
@@ -393,7 +415,11 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
             }
             if (qpos < 0 && pmin == ~0ull) break;
             if (qkey <= pmin) {
-              if (lane == 0) { qa[qpos] |= kCheckedBit; s_cid[cnt] = static_cast<int>(key_id(qkey)); }
+              if (lane == 0) {
+                qa[qpos] |= kCheckedBit;
+                ubits[qpos >> 5] &= ~(1u << (qpos & 31));
+                s_cid[cnt] = static_cast<int>(key_id(qkey));
+              }
               sp = qpos + 1;
             } else {
               // keys are distinct: exactly one lane owns the pending minimum and marks it
@@ -502,7 +528,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     // ---- results + visited reset (:711-714) ----
     {
       const int m = s_npend;  // only checked entries can be left (the last pick found nothing unchecked)
-      if (m > 0) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor);
+      if (m > 0) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor, ubits);
     }
     unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
     for (int i = tid; i < L; i += kGsThreads) out[i] = qa[i];
@@ -618,7 +644,7 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   const int fc = next_pow2(std::max(width * kEll, kGsThreads) + kMaxR);
   auto smem_for = [&](int r) {
     return static_cast<size_t>(r) * slot_bytes + static_cast<size_t>(Lp) * 8 + 2 * kPC * 8 + kMaxR * 8 +
-           static_cast<size_t>(dimp) * 4 + kPC * 4 + static_cast<size_t>(fc) * 4 + kMaxR * 4;
+           static_cast<size_t>(dimp) * 4 + kPC * 4 + static_cast<size_t>(fc) * 4 + kMaxR * 4 + static_cast<size_t>((Lp + 31) / 32) * 4;
   };
   while (R > 2 && smem_for(R) > 200 * 1024) --R;
   if (smem_for(R) > 226 * 1024) return fail(EPS_ERR_UNSUPPORTED, "queue + query + row ring do not fit in shared memory");
