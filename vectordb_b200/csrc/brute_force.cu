@@ -15,6 +15,8 @@
 //   * bf_dist_tile_kernel  — large batches: 128x128x16 shared-memory tiles, 8x8 register micro-tiles.
 //     FP32-pipe bound (2*N*d*B FMA-class ops, 3 for L2).
 // followed by bf_select_kernel: threshold-filtered streaming top-k per (query, row-split).
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace eps {
@@ -495,7 +497,8 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
   const bool use_tc = allow_tc && n >= 4096 && self_base < 0 && !dyn_filter && tc_dist_usable(ix, nq) && d_queries != ix->d_vectors;
   if (use_tc) {
     // k' coarse candidates per query: k + max(118, k) (128 for top-10), times the boost the guard has learnt
-    k = std::min<int64_t>(8192, (k_final + std::max<int64_t>(118, k_final)) * std::max(1, ix->coarse_boost));
+    static const int64_t env_kmin = [] { const char* e = getenv("EPS_SCAN_KMIN"); return e ? atoll(e) : 118ll; }();  // developer knob
+    k = std::min<int64_t>(8192, (k_final + std::max<int64_t>(env_kmin, k_final)) * std::max(1, ix->coarse_boost));
     EPS_TRY(ix->s_coarse.reserve(static_cast<size_t>(nq) * k * 8));
     d_topk = ix->s_coarse.as<unsigned long long>();
   }
@@ -570,7 +573,9 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     // select from), then fused launches grow 8x at a time as the thresholds tighten: expected survivors per query
     // of a launch ~ k' * rows_in_launch / rows_seen_so_far = 8 k' << candidate capacity
     int64_t want_rows = chunk;
-    if (use_tc) want_rows = fused ? std::min<int64_t>(8 * c0, 4 * 1024 * 1024) : std::min<int64_t>(chunk, 4 * 1024);
+    static const int64_t env_boot = [] { const char* e = getenv("EPS_SCAN_BOOT"); return e ? atoll(e) : 4096ll; }();   // developer knobs,
+    static const int64_t env_grow = [] { const char* e = getenv("EPS_SCAN_GROW"); return e ? atoll(e) : 8ll; }();      // read once
+    if (use_tc) want_rows = fused ? std::min<int64_t>(env_grow * c0, 4 * 1024 * 1024) : std::min<int64_t>(chunk, env_boot);
     const int64_t cn = std::min(want_rows, n - c0);
     SelectArgs a;
     a.ldd = chunk; a.row_base = row_start + c0; a.nsplit = nsplit; a.k = static_cast<int>(k); a.state = state;
