@@ -682,6 +682,9 @@ def main():
             if good_graph:
                 graph = ix.get_graph()
                 L = mode[1] if mode[0] == "graph" else good_graph[0]["L"]
+                deg = np.diff(graph[1])
+                out["graph_stats"] = {"edges": int(graph[1][-1]), "avg_degree": float(deg.mean()), "nav_degree": int(deg[graph[3]]),
+                                      "max_degree_other": int(np.delete(deg, graph[3]).max())}
             nqc = min(a.cpu_queries, a.batch)
             Qc = np.stack([A.Qpool[0][:nqc].cpu().numpy(), A.Qpool[1 % n_pool][:nqc].cpu().numpy()]).astype(np.float32)
             res = run_reference_child(a, graph, L, Qc, timeout=a.cpu_timeout)
