@@ -19,17 +19,18 @@ for dist in dists:
     oi = torch.empty((nq, k), dtype=torch.int64, device=dev); od = torch.empty((nq, k), dtype=torch.float32, device=dev)
     oc = torch.empty((nq,), dtype=torch.int64, device=dev)
     ix.config(512, 512, force_brute=True)
-    for mode in ("bf16", "tf32"):
-        for guard in (1, 0):
+    for mode in os.environ.get("MODES", "bf16,tf32").split(","):
+        for guard in [int(x) for x in os.environ.get("GUARDS", "1,0").split(",")]:
             ix.set_coarse(mode); ix.set_coarse_guard(guard)
-            for _ in range(3):
+            for _ in range(int(os.environ.get("WARM", "3"))):
                 ix.search_device(Q.data_ptr(), nq, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr())
             ms = 0.0
-            for _ in range(5):
+            reps = int(os.environ.get("REPS", "5"))
+            for _ in range(reps):
                 st = ix.search_device(Q.data_ptr(), nq, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), want_stats=True)
                 ms += st["total_ms"]
-            print(json.dumps({"dist": dist, "coarse": mode, "guard": guard, "ms_per_step": ms / 5, "kernel_ms": st["kernel_ms"],
+            print(json.dumps({"dist": dist, "coarse": mode, "guard": guard, "ms_per_step": ms / reps, "kernel_ms": st["kernel_ms"],
                               "launches": st["kernel_launches"], "n_redone": st["n_redone"],
-                              "TFLOPs": 2.0 * rows * nq * dim / (ms / 5 / 1e3) / 1e12}))
+                              "TFLOPs": 2.0 * rows * nq * dim / (ms / reps / 1e3) / 1e12}))
     ix.close(); del X, Q
     torch.cuda.empty_cache()
