@@ -69,7 +69,7 @@ def parse():
     p.add_argument("--ring", type=int, default=0, help="graph kernel: TMA row-ring slots per CTA (0 = auto)")
     p.add_argument("--ctas", type=int, default=0, help="graph kernel: resident CTAs per SM (0 = auto)")
     p.add_argument("--knn-k", type=int, default=64)
-    p.add_argument("--nnd-iters", type=int, default=10)
+    p.add_argument("--nnd-iters", type=int, default=14)
     p.add_argument("--uniform-record", type=int, default=1, help="also measure the iid-uniform table (exact scan)")
     p.add_argument("--uniform-graph", action="store_true", help="also build + search a graph on the iid-uniform table")
     p.add_argument("--shard-rows", action="store_true")
@@ -685,7 +685,7 @@ def main():
                 deg = np.diff(graph[1])
                 out["graph_stats"] = {"edges": int(graph[1][-1]), "avg_degree": float(deg.mean()), "nav_degree": int(deg[graph[3]]),
                                       "max_degree_other": int(np.delete(deg, graph[3]).max())}
-            nqc = min(a.cpu_queries, a.batch)
+            nqc = min(a.cpu_queries, a.batch) if graph is not None else min(8, a.batch)  # the reference's brute-force branch is slow
             Qc = np.stack([A.Qpool[0][:nqc].cpu().numpy(), A.Qpool[1 % n_pool][:nqc].cpu().numpy()]).astype(np.float32)
             res = run_reference_child(a, graph, L, Qc, timeout=a.cpu_timeout)
             modes_qps = {m: float(x["qps"][-1]) for m, x in res["modes"].items()}

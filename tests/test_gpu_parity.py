@@ -390,7 +390,7 @@ def test_nn_descent_build_quality(vdb, m):
         ni, off, nb, nav = ix.get_graph()
         deg = np.diff(off)
         others = np.delete(deg, nav)  # the navigation point also carries the entries of otherwise unreachable components
-        assert ni == n and deg.min() >= 1 and others.max() <= 50 + 64 and deg[nav] <= 50 + 256, (name, others.max(), deg[nav])
+        assert ni == n and deg.min() >= 1 and others.max() <= 50 + 16, (name, others.max(), deg[nav])
         ix.config(200, 200)
         ix.set_search_width(1)
         ids, _, _, st = ix.search(Q, 10)
@@ -428,7 +428,7 @@ def test_build_repair_does_not_grow_hubs(vdb):
     ix.build(n, knn_k=64, nnd_iters=8)
     ni, off, nb, nav = ix.get_graph()
     deg = np.diff(off)
-    assert np.delete(deg, nav).max() <= 50 + 64 and deg[nav] <= 50 + 256, (np.delete(deg, nav).max(), deg[nav])
+    assert np.delete(deg, nav).max() <= 50 + 16, (np.delete(deg, nav).max(), deg[nav])
     # every vertex reachable from the navigation point
     seen = np.zeros(n, bool)
     seen[nav] = True

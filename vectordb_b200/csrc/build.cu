@@ -332,17 +332,17 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
   //   1. u's own kNN list (exact near neighbours, already on hand): the nearest linked entry that has received fewer
   //      than kRepairCap repair edges so far (on inner-product tables the kNN lists of most vertices point at the same
   //      few large-norm rows; without the cap one of them collects O(n) repair edges);
-  //   2. NO kNN entry of u is linked: u's neighbourhood is a component of its own and u becomes its ENTRY.  Up to
-  //      kStar entries hang directly off the navigation point, i.e. are part of every search's seed set
-  //      (PrepareInitIds starts from the navigation point's out-neighbours).  With more components than that a
-  //      routing layer keeps the seed set small: kStar entries ("hubs") hang off the navigation point and every
-  //      other entry hangs off its nearest hub (exact L2, one small distance tile on the device) — the hub nearest
-  //      to a query is expanded first and brings the entries of the components around it;
+  //   2. NO kNN entry of u is linked: u's neighbourhood is a component of its own and u becomes its ENTRY, an
+  //      out-neighbour of the navigation point, i.e. part of every search's seed set (PrepareInitIds starts from the
+  //      navigation point's out-neighbours) as long as the queue length covers the navigation point's degree.
+  //      (A routing layer — 256 hub entries off the navigation point, every other entry off its nearest hub — was
+  //      tried and dropped: with well-separated clusters in 768-d all hubs are about equally far from a query, best-
+  //      first search cannot tell which hub leads to the query's component, recall fell from 0.99 to 0.89 at L = 2048.)
   //   3. the reference's own pool: the un-repaired graph is installed and the rows of the still unlinked vertices go
   //      through graph_search on the device (L2 like the rest of the refinement, beam = max(64, search_length));
   //   4. a random linked vertex (:767-774).
   // The attach / flood bookkeeping — integer work — runs on the host in the reference's order.
-  constexpr size_t kRepairCap = 16, kStar = 256;
+  constexpr size_t kRepairCap = 16;
   std::vector<int32_t> entries;  // one per component that the kNN lists do not connect to the rest
   std::vector<std::vector<int32_t>> extra(static_cast<size_t>(n));  // edges added by the repair
   {
@@ -449,52 +449,8 @@ int build_graph(Index* ix, int64_t n, const eps_build_params* params) {
       if (rc != EPS_OK) return rc;
     }
   }
-  // ---- entries of the separate components: star below kStar, hub routing layer above ----
-  if (entries.size() <= kStar) {
-    for (int32_t u : entries) extra[nav].push_back(u);
-  } else {
-    std::vector<int32_t> hubs, rest;
-    for (size_t i = 0; i < kStar; ++i) hubs.push_back(entries[i * entries.size() / kStar]);
-    {
-      std::vector<uint8_t> is_hub(static_cast<size_t>(n), 0);
-      for (int32_t h : hubs) is_hub[h] = 1;
-      for (int32_t u : entries) if (!is_hub[u]) rest.push_back(u);
-    }
-    for (int32_t h : hubs) extra[nav].push_back(h);
-    const int64_t nh = static_cast<int64_t>(hubs.size()), chunk = 8192, ldd = (nh + 3) & ~3ll;
-    DevBuf d_ids, d_h, d_q, d_D;
-    EPS_TRY(d_ids.reserve(static_cast<size_t>(std::max<int64_t>(nh, chunk)) * 4));
-    EPS_TRY(d_h.reserve(static_cast<size_t>(nh) * ix->dim * 4));
-    EPS_TRY(d_q.reserve(static_cast<size_t>(chunk) * ix->dim * 4));
-    EPS_TRY(d_D.reserve(static_cast<size_t>(chunk) * ldd * 4));
-    EPS_CUDA(cudaMemcpyAsync(d_ids.p, hubs.data(), static_cast<size_t>(nh) * 4, cudaMemcpyHostToDevice, ix->stream));
-    EPS_TRY(gather_rows(ix, d_ids.as<int32_t>(), nh, d_h.as<float>()));
-    EPS_CUDA(cudaStreamSynchronize(ix->stream));
-    std::vector<float> h_D(static_cast<size_t>(chunk) * ldd);
-    const int saved_metric = ix->metric;
-    int rc = EPS_OK;
-    for (size_t c0 = 0; c0 < rest.size() && rc == EPS_OK; c0 += static_cast<size_t>(chunk)) {
-      const int64_t cn = static_cast<int64_t>(std::min<size_t>(static_cast<size_t>(chunk), rest.size() - c0));
-      uint64_t launches = 0;
-      ix->metric = EPS_METRIC_L2;
-      if (cudaMemcpyAsync(d_ids.p, rest.data() + c0, static_cast<size_t>(cn) * 4, cudaMemcpyHostToDevice, ix->stream) != cudaSuccess)
-        rc = fail(EPS_ERR_CUDA, "routing layer: id upload failed");
-      if (rc == EPS_OK) rc = gather_rows(ix, d_ids.as<int32_t>(), cn, d_q.as<float>());
-      if (rc == EPS_OK) rc = launch_distances(ix, d_h.as<float>(), 0, nh, d_q.as<float>(), cn, d_D.as<float>(), ldd, &launches);
-      ix->metric = saved_metric;
-      if (rc == EPS_OK && (cudaMemcpyAsync(h_D.data(), d_D.p, static_cast<size_t>(cn) * ldd * 4, cudaMemcpyDeviceToHost, ix->stream) != cudaSuccess ||
-                           cudaStreamSynchronize(ix->stream) != cudaSuccess))
-        rc = fail(EPS_ERR_CUDA, "routing layer: distance tile failed");
-      if (rc != EPS_OK) break;
-      for (int64_t i = 0; i < cn; ++i) {
-        const float* row = &h_D[static_cast<size_t>(i) * ldd];
-        int64_t best = 0;
-        for (int64_t j = 1; j < nh; ++j) if (row[j] < row[best]) best = j;
-        extra[hubs[best]].push_back(rest[c0 + i]);
-      }
-    }
-    if (rc != EPS_OK) return rc;
-  }
+  // ---- entries of the separate components: out-neighbours of the navigation point ----
+  for (int32_t u : entries) extra[nav].push_back(u);
 
   std::vector<int64_t> off(static_cast<size_t>(n) + 1);
   int64_t e = 0;
