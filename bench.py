@@ -7,13 +7,20 @@ roofline fraction of the dominant kernel and with the reference's own CPU path t
   python bench.py [--gpus N --steps K --warmup W] [--impl reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload.  SURVEY.md §8d defines two synthetic distributions: iid uniform[0,1) and a clustered one (1024 Gaussian
-centres, sigma = 0.1).  A graph index only has a recall >= 0.99 operating point on data with neighbourhood structure
-(on iid-uniform 768-d data the reference itself touches 75-95 % of a table for recall 0.99 and graph search at
-L = 2048 finds 30 % of the neighbours), so the HEADLINE workload is the clustered table — there the path
-north_star names (persistent-CTA graph search, HBM-bound) competes with the exact scan (tensor-bound) and the
-fastest mode with recall >= 0.99 is `value`; the iid-uniform table is measured in the same run and printed as the
-"uniform" record (exact scan; graph recall is listed when --uniform-graph is given).
+Workload.  Three synthetic 10M x 768 tables (random floats, seeded, generated on the device):
+  * "manifold" (headline, --dist): 1024 overlapping unit Gaussians in a 32-d latent space, mapped into R^768 by a
+    fixed orthonormal map, plus isotropic noise — clustered data of low intrinsic dimension, the structure embedding
+    tables have and the case a graph index exists for (queue length L of a few hundred reaches recall 0.99);
+  * "cluster": SURVEY.md §8d's clustered table, 1024 centres with ISOTROPIC sigma = 0.1 blobs in all 768 dimensions.
+    Distances inside a blob concentrate, so recall 0.99 means visiting the query's whole 9.8k-row blob, and the 1024
+    blobs are separate graph components that the search can only enter through the navigation point's > 1000
+    out-neighbours: L >= 1536 (PrepareInitIds seeds exactly L of them).  Graph search still beats the exact scan;
+  * "uniform": SURVEY.md §8d's iid uniform[0,1) table.  No neighbourhood structure at all (the reference itself
+    touches 75-95 % of the table for recall 0.99; graph search at L = 2048 finds 30 % of the neighbours): measured
+    with the exact scan.
+`value` is the fastest mode (graph at the smallest L of the sweep that reaches the target, or the exact scan) with
+recall@10 >= 0.99 on the --dist table; the other two tables are measured in the same run (N = 1) and printed as the
+"cluster" / "uniform" records with their own recall, QPS and rooflines.
 
 One "step" = one pass of the hot path over one batch of 1024 queries per GPU.  A step is timed with CUDA events on
 the index's launch stream, bracketed by barrier + synchronize, MAX over ranks.  `value` has the queries already
@@ -61,16 +68,17 @@ def parse():
     p.add_argument("--batch", type=int, default=1024)
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--metric", default="l2")
-    p.add_argument("--dist", default="cluster", choices=["uniform", "cluster"])
+    p.add_argument("--dist", default="manifold", choices=["uniform", "cluster", "manifold"])
     p.add_argument("--centers", type=int, default=1024)
     p.add_argument("--modes", default="graph,brute-bf16", help="candidate modes: graph, brute-bf16, brute-tf32, brute-fp32")
-    p.add_argument("--L-sweep", default="256,512,1024,1536,2048,3072,4096", help="graph queue lengths, ascending; stops at the first that reaches the recall target")
+    p.add_argument("--L-sweep", default="128,192,256,384,512,768,1024,1536,2048,3072,4096", help="graph queue lengths, ascending; stops at the first that reaches the recall target")
     p.add_argument("--width", type=int, default=6, help="graph search width (1 = the reference's sequential order)")
     p.add_argument("--ring", type=int, default=0, help="graph kernel: TMA row-ring slots per CTA (0 = auto)")
     p.add_argument("--ctas", type=int, default=0, help="graph kernel: resident CTAs per SM (0 = auto)")
     p.add_argument("--knn-k", type=int, default=64)
     p.add_argument("--nnd-iters", type=int, default=14)
-    p.add_argument("--uniform-record", type=int, default=1, help="also measure the iid-uniform table (exact scan)")
+    p.add_argument("--extra-tables", default="cluster,uniform", help="other SURVEY 8d tables measured in the same run at N=1 "
+                   "(cluster: graph + exact scan; uniform: exact scan, + graph with --uniform-graph); '' = none")
     p.add_argument("--uniform-graph", action="store_true", help="also build + search a graph on the iid-uniform table")
     p.add_argument("--shard-rows", action="store_true")
     p.add_argument("--recall-target", type=float, default=0.99)
@@ -90,25 +98,53 @@ def parse():
 # a seeded Philox stream; the CPU generator of the same seed is a different stream and is only used when no GPU
 # is present, i.e. in the CPU contract test)
 # ------------------------------------------------------------------------------------------------------
+LATENT_DIM = int(os.environ.get("EPS_BENCH_LATENT", "32"))      # "manifold" tables: dimension of the latent space
+LATENT_SPREAD = float(os.environ.get("EPS_BENCH_SPREAD", "1.5"))  # std of the mixture centres, in units of the blob std
+LATENT_NOISE = float(os.environ.get("EPS_BENCH_NOISE", "0.05"))   # isotropic noise added in the full space
+
+
+def _mixture(dim, dist, device, centers_n):
+    """Fixed (seed 44) parameters of the synthetic tables.  "cluster": centres uniform in the unit cube, isotropic blobs
+    of std 0.1 in all `dim` dimensions (distances concentrate: the hardest case for any graph index).  "manifold": a
+    mixture of overlapping unit Gaussians in a LATENT_DIM-dimensional latent space, mapped into R^dim by a fixed linear
+    map with orthonormal rows, plus small isotropic noise — low intrinsic dimension, as embedding tables have."""
+    import torch
+    gc = torch.Generator(device=device)
+    gc.manual_seed(44)
+    if dist == "cluster":
+        return torch.rand((centers_n, dim), generator=gc, device=device), None
+    lat = torch.randn((centers_n, LATENT_DIM), generator=gc, device=device) * LATENT_SPREAD
+    a = torch.randn((dim, LATENT_DIM), generator=gc, device=device)
+    q, _ = torch.linalg.qr(a)  # dim x LATENT_DIM, orthonormal columns
+    return lat, q.T.contiguous()
+
+
+def _draw(out, dist, g, device, centers, umap):
+    import torch
+    n, dim = out.shape
+    if dist == "uniform":
+        out.uniform_(0.0, 1.0, generator=g)
+        return
+    lab = torch.randint(0, centers.shape[0], (n,), generator=g, device=device)
+    if dist == "cluster":
+        out.normal_(0.0, 0.1, generator=g)
+        out += centers[lab]
+        return
+    z = torch.randn((n, LATENT_DIM), generator=g, device=device)
+    z += centers[lab]
+    out.normal_(0.0, LATENT_NOISE, generator=g)
+    out.addmm_(z, umap)
+
+
 def gen_table(rows, dim, dist, seed, device, centers_n=1024):
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     X = torch.empty((rows, dim), dtype=torch.float32, device=device)
-    centers = None
-    if dist == "cluster":
-        gc = torch.Generator(device=device)
-        gc.manual_seed(44)
-        centers = torch.rand((centers_n, dim), generator=gc, device=device)
+    centers, umap = (None, None) if dist == "uniform" else _mixture(dim, dist, device, centers_n)
     step = 1_000_000
     for r0 in range(0, rows, step):
-        r1 = min(rows, r0 + step)
-        if dist == "uniform":
-            X[r0:r1].uniform_(0.0, 1.0, generator=g)
-        else:
-            lab = torch.randint(0, centers_n, (r1 - r0,), generator=g, device=device)
-            X[r0:r1].normal_(0.0, 0.1, generator=g)
-            X[r0:r1] += centers[lab]
+        _draw(X[r0:min(rows, r0 + step)], dist, g, device, centers, umap)
     return X
 
 
@@ -116,13 +152,10 @@ def gen_queries(n, dim, dist, seed, device, centers_n=1024):
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    if dist == "uniform":
-        return torch.rand((n, dim), generator=g, device=device)
-    gc = torch.Generator(device=device)
-    gc.manual_seed(44)
-    centers = torch.rand((centers_n, dim), generator=gc, device=device)
-    lab = torch.randint(0, centers_n, (n,), generator=g, device=device)
-    return centers[lab] + 0.1 * torch.randn((n, dim), generator=g, device=device)
+    Q = torch.empty((n, dim), dtype=torch.float32, device=device)
+    centers, umap = (None, None) if dist == "uniform" else _mixture(dim, dist, device, centers_n)
+    _draw(Q, dist, g, device, centers, umap)
+    return Q
 
 
 class ClockSampler:
@@ -186,7 +219,11 @@ def measured_peaks():
 
 
 def workload_name(a, extra=""):
-    data = "iid-uniform[0,1)" if a.dist == "uniform" else "clustered (%d Gaussian centres, sigma=0.1)" % a.centers
+    data = {"uniform": "iid-uniform[0,1)",
+            "cluster": "clustered, isotropic (%d Gaussian centres in the unit cube, sigma=0.1 in all %d dimensions)" % (a.centers, a.dim),
+            "manifold": "clustered, low intrinsic dimension (%d unit Gaussians, centre std %.1f, in a %d-d latent space mapped "
+                        "to R^%d by a fixed orthonormal map, + isotropic noise sigma=%.2f)" % (
+                            a.centers, LATENT_SPREAD, LATENT_DIM, a.dim, LATENT_NOISE)}[a.dist]
     return "%dx%d f32 %s %s (seed 42), batch=%d, top-%d%s" % (a.rows, a.dim, a.metric, data, a.batch, a.k, extra)
 
 
@@ -711,15 +748,40 @@ def main():
             out["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference",
                                    "sample": "failed: %r" % (e,)}
 
-    # ---- the iid-uniform table of SURVEY.md §8d in the same run ----
-    if a.uniform_record and a.dist != "uniform" and group is None:
+    # ---- the other tables of SURVEY.md §8d in the same run (N = 1: replicas would only repeat them) ----
+    for t in [x.strip() for x in a.extra_tables.split(",") if x.strip()]:
+        if t == a.dist or group is not None or world > 1:
+            continue
         try:
             A.close()
             torch.cuda.empty_cache()
             au = argparse.Namespace(**vars(a))
-            au.dist = "uniform"
-            A = Arena(au, "uniform", dev, local, rank, world)
+            au.dist = t
+            A = Arena(au, t, dev, local, rank, world)
             A.ground_truth()
+            trep = {"workload": workload_name(au)}
+            if t != "uniform" or a.uniform_graph:
+                t0 = time.perf_counter()
+                A.ix.build(rows, knn_k=a.knn_k, nnd_iters=a.nnd_iters)
+                torch.cuda.synchronize()
+                trep["graph_build_s"] = time.perf_counter() - t0
+                sweep = []
+                for L in [int(x) for x in a.L_sweep.split(",")]:
+                    if L < 1024 and t == "cluster":  # the navigation point alone has > 1000 out-neighbours there
+                        continue
+                    gm = ("graph", L, "")
+                    A.set_mode(gm)
+                    A.search(A.Qpool[0])
+                    grec = recall_of(A.truth, A.out_ids, a.k)
+                    sweep.append({"L": L, key_rec: grec})
+                    if grec >= a.recall_target or L >= 2048:
+                        break
+                timed_device_steps(gm, a.warmup, 0)
+                ms, st = timed_device_steps(gm, min(a.steps, 5), a.warmup)
+                k_ms = float(sum(x["kernel_ms"] for x in st))
+                ag = {k: float(sum(x[k] for x in st)) for k in ("n_dist", "n_seed", "n_expand", "n_edges")}
+                trep["graph"] = {"value": a.batch * len(st) / (ms / 1000.0), "unit": "queries/s", "L": gm[1], "width": a.width,
+                                 key_rec: grec, "roofline": graph_roofline(ag, gm[1], k_ms, len(st)), "L_sweep": sweep}
             m = ("brute", 0, "bf16")
             A.set_mode(m)
             A.search(A.Qpool[0])
@@ -727,24 +789,13 @@ def main():
             umiss = classify_misses(A.truth.cpu().numpy(), A.truth_d.cpu().numpy(), A.out_ids.cpu().numpy(), A.out_d.cpu().numpy(), a.k)
             timed_device_steps(m, a.warmup, 0)
             ms, st = timed_device_steps(m, min(a.steps, 5), a.warmup)
-            k_ms = float(sum(s["kernel_ms"] for s in st))
-            urep = {"workload": workload_name(au, ", exact scan (tcgen05 bf16 coarse pass + fp32 re-score)"),
-                    "value": world * a.batch * len(st) / (ms / 1000.0), "unit": "queries/s", key_rec: urec,
-                    "roofline": scan_roofline("bf16", k_ms, len(st)), "misses_vs_fp32": umiss}
-            if a.uniform_graph:
-                t0 = time.perf_counter()
-                A.ix.build(rows, knn_k=a.knn_k, nnd_iters=a.nnd_iters)
-                torch.cuda.synchronize()
-                urep["graph_build_s"] = time.perf_counter() - t0
-                gm = ("graph", 2048, "")
-                A.set_mode(gm)
-                A.search(A.Qpool[0])
-                grec = recall_of(A.truth, A.out_ids, a.k)
-                ms, st = timed_device_steps(gm, 3, a.warmup)
-                urep["graph_L2048"] = {key_rec: grec, "value": world * a.batch * len(st) / (ms / 1000.0)}
-            out["uniform"] = urep
+            k_ms = float(sum(x["kernel_ms"] for x in st))
+            trep["exact_scan_bf16"] = {"value": a.batch * len(st) / (ms / 1000.0), "unit": "queries/s", key_rec: urec,
+                                       "roofline": scan_roofline("bf16", k_ms, len(st)), "misses_vs_fp32": umiss,
+                                       "queries_redone_by_guard_per_step": float(np.mean([x["n_redone"] for x in st]))}
+            out[t] = trep
         except Exception as e:
-            out["uniform"] = {"failed": repr(e)}
+            out[t] = {"failed": repr(e)}
     if rank == 0:
         print(json.dumps(out))
     if group is not None:

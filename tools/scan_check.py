@@ -10,9 +10,10 @@ rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 dists = sys.argv[2:] or ["uniform", "cluster"]
 dim, nq, k = 768, 1024, 10
 dev = torch.device("cuda", 0)
+centers = int(os.environ.get("CENTERS", "1024"))
 for dist in dists:
-    X = gen_table(rows, dim, dist, 42, dev)
-    Q = gen_queries(nq, dim, dist, 43, dev)
+    X = gen_table(rows, dim, dist, 42, dev, centers)
+    Q = gen_queries(nq, dim, dist, 43, dev, centers)
     ix = vectordb_b200.Index("l2", dim, capacity=rows)
     ix.adopt_device_rows(X.data_ptr(), rows)
     torch.cuda.synchronize()
