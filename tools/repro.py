@@ -11,20 +11,21 @@ from bench import gen_table, gen_queries
 
 what, rows, dim, centers = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 dev = torch.device("cuda", 0)
-X = gen_table(rows, dim, "cluster", 42, dev, centers)
+DIST = os.environ.get("DIST", "cluster")
+X = gen_table(rows, dim, DIST, 42, dev, centers)
 nq, k = int(os.environ.get("NQ", "1024")), 10
-Q = gen_queries(nq, dim, "cluster", 43, dev, centers)
+Q = gen_queries(nq, dim, DIST, 43, dev, centers)
 ix = vectordb_b200.Index("l2", dim, capacity=rows)
 ix.adopt_device_rows(X.data_ptr(), rows)
 torch.cuda.synchronize()  # generators done before the library stream reads
-path = "/tmp/repro_graph_%d_%d_%d.npz" % (rows, dim, centers)
+path = "/tmp/repro_graph_%s_%d_%d_%d.npz" % (DIST, rows, dim, centers)
 if what == "build":
     t0 = time.perf_counter()
-    ix.build(rows, knn_k=64, nnd_iters=10)
+    ix.build(rows, knn_k=64, nnd_iters=int(os.environ.get("NND_ITERS", "10")))
     n, off, nb, nav = ix.get_graph()
     deg = np.diff(off)
     print("build %.1f s, edges %d, avg deg %.1f, max deg %d" % (time.perf_counter() - t0, off[-1], deg.mean(), deg.max()))
-    np.savez(path, off=off, nb=nb.astype(np.int32), nav=nav)
+    np.savez(path, off=off, nb=np.asarray(nb, dtype=np.int32), nav=nav)
     sys.exit(0)
 g = np.load(path)
 ix.set_graph(rows, g["off"], g["nb"].astype(np.int64), int(g["nav"]))

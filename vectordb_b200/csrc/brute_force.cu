@@ -556,6 +556,20 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     EPS_CUDA(cudaFuncSetAttribute(bf_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
   }
   const int cand_cap = static_cast<int>(std::max<int64_t>(4096, 16 * k));  // fused launches grow 8x: ~8 k' survivors each
+#ifdef EPS_GS_PROFILE
+  // developer build: event after every launch of the tensor-core scan, printed as a timeline at the end
+  std::vector<std::pair<std::string, cudaEvent_t>> tl;
+  auto mark = [&](const std::string& name) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, ix->stream);
+    tl.push_back({name, e});
+  };
+#define TL_MARK(x) mark(x)
+#else
+#define TL_MARK(x) do { } while (0)
+#endif
+  TL_MARK("start");
   int* d_overflow = nullptr;
   if (use_tc) {
     EPS_TRY(ix->s_thr.reserve(static_cast<size_t>(nq) * 4));
@@ -586,16 +600,21 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
       if (use_tc) EPS_TRY(tc_launch_distances(ix, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
       else EPS_TRY(launch_distances(ix, ix->d_vectors, row_start + c0, cn, d_queries, nq, D, chunk, &launches));
       a.D = D; a.keys_in = nullptr; a.n = cn;
+      TL_MARK("dist tile " + std::to_string(cn));
       bf_select_kernel<false><<<dim3(static_cast<unsigned>(nq), nsplit), kSelThreads, sel_smem, ix->stream>>>(a);
+      TL_MARK("select");
     } else {
       EPS_CUDA(cudaMemsetAsync(ix->s_cand_cnt.p, 0, static_cast<size_t>(nq) * 4, ix->stream));
       TcFused f;
       f.thr = ix->s_thr.as<float>(); f.cand = ix->s_cand.as<unsigned long long>(); f.cand_cnt = ix->s_cand_cnt.as<int>();
       f.pass = d_pass; f.pass_base = row_start; f.cand_cap = cand_cap;
+      TL_MARK("memset");
       EPS_TRY(tc_launch_distances(ix, row_start + c0, cn, d_queries, nq, nullptr, 0, &launches, &f));
+      TL_MARK("fused " + std::to_string(cn));
       a.D = nullptr; a.keys_in = f.cand; a.n = cand_cap; a.counts = f.cand_cnt; a.overflow = d_overflow;
       a.pass = nullptr; a.dyn = nullptr;
       bf_select_kernel<true><<<dim3(static_cast<unsigned>(nq), 1), kSelThreads, sel_smem, ix->stream>>>(a);
+      TL_MARK("merge");
     }
     ++launches;
     EPS_CUDA(cudaGetLastError());
@@ -626,8 +645,23 @@ static int topk_impl(Index* ix, const float* d_queries, int64_t nq, int64_t row_
     }
     // ONE host round trip per tensor-core scan: candidate-buffer overflow (adversarial row order: the buffers are
     // sized for the expected survivors) and the guard's verdict
+    TL_MARK("rescore+verify");
     EPS_CUDA(cudaMemcpyAsync(h_state, d_overflow, 8, cudaMemcpyDeviceToHost, ix->stream));
     EPS_CUDA(cudaStreamSynchronize(ix->stream));
+#ifdef EPS_GS_PROFILE
+    if (use_tc && tl.size() > 1 && n >= 1000000) {
+      fprintf(stderr, "[scan-timeline]");
+      for (size_t i = 1; i < tl.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tl[i - 1].second, tl[i].second);
+        fprintf(stderr, " %s %.3f |", tl[i].first.c_str(), ms);
+      }
+      float tot = 0.f;
+      cudaEventElapsedTime(&tot, tl.front().second, tl.back().second);
+      fprintf(stderr, " total %.3f ms\n", tot);
+    }
+    for (auto& t : tl) cudaEventDestroy(t.second);
+#endif
     if (stats) stats->kernel_launches += launches;
     if (h_state[0]) {  // never silently truncated: the call is redone on the fp32 path
       if (stats) stats->n_redone += static_cast<uint64_t>(nq);

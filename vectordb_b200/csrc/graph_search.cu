@@ -69,6 +69,8 @@ struct GSArgs {
   const float* seed_dist;         // [nq x seed_ld] distances of the seed set (dense tile product)
   const float* queries;
   uint32_t* visited;              // [slots x visited_words]
+  int32_t* vlog;                  // [slots x vlog_cap] ids whose bit the running query has set, in FIFO order (visited reset)
+  int vlog_cap;
   unsigned long long* out_queue;  // [nq x L]
   int* work_counter;
   unsigned long long* stats;      // n_dist, n_expand, n_edges
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
   const uint32_t ring0 = smem_u32(ring), bar0 = smem_u32(bars);
   const uint32_t row_bytes = static_cast<uint32_t>(a.dim) * 4u;
   uint32_t* visited = a.visited + static_cast<int64_t>(blockIdx.x) * a.visited_words;
+  int32_t* vlog = a.vlog + static_cast<int64_t>(blockIdx.x) * a.vlog_cap;
 
   if (tid == 0) {
     for (int s = 0; s < R; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -285,7 +288,9 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     const int q = s_q;
     if (q >= a.nq) break;
 #ifdef EPS_GS_PROFILE
-    if (tid == 0 && a.qtimes) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.qtimes[2 * q] = t; }
+    if (tid == 0 && a.qtimes) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.qtimes[4 * q] = t; }
+    const unsigned long long prof_nd0 = st_ndist;
+    unsigned long long prof_iters = 0;
 #endif
 
     // ---- seed (InitializeSetLPara): precomputed distances of the query-independent seed set ----
@@ -310,6 +315,9 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
 
     // ---- best-first loop (SearchImpl) ----
     for (;;) {
+#ifdef EPS_GS_PROFILE
+      ++prof_iters;
+#endif
       // barrier X: pending appends, FIFO writes and slot states of the previous iteration are settled;
       // the count is the number of ring slots with a row in flight
       GS_T(tx0);
@@ -332,37 +340,50 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       // has been consumed and merged (exact)
       const bool want = a.exact ? idle : (fifo_tail - head) < static_cast<uint32_t>(R);
 
-      // -- C/B, per consumer warp: distances of the landed rows of its slots, then refill every slot from the FIFO --
+      // -- C/B, per consumer warp: distances of the landed rows of its slots, then refill every slot from the FIFO.
+      // The warp keeps streaming (consume, refill, consume ...) without coming back to the block barrier while the FIFO
+      // has a backlog and the pending buffer has room: its slots stay in flight for the whole backlog instead of one ring
+      // pass per block iteration.  It leaves with its last refills in flight, so that the pick / adjacency / visited
+      // phases below overlap them.  Accepting against the bound of the last merge only lets more keys into the pending
+      // buffer (the bound never grows); the merge evicts them, so the queue after the merge is the same.
       if (n_own > 0) {
         const unsigned long long bound = qa[L - 1] & kKeyMask;  // worst entry as of the last merge (:546)
-        if (occ_mask) {
-          GS_T(tw0);
-          if (n_own <= 1) consume_slots<1>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
-          else if (n_own <= 2) consume_slots<2>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
-          else if (n_own <= 4) consume_slots<4>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
-          else consume_slots<8>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
-          par_mask ^= occ_mask;
-          GS_T(tw1);
-          GS_ACC(3, tw0, tw1);
-        }
-        __syncwarp();  // every lane has finished reading the slots
-        bool got = false;
-        if (lane < n_own) {
-          const unsigned idx = atomicAdd(&s_head, 1u);
-          if (idx >= fifo_tail) atomicSub(&s_head, 1u);  // nothing left: hand the index back
-          else {
-            const int slot = cw + 3 * lane;
-            const int id = fifo[idx & fmask];
-            slot_id[slot] = id;
-            got = true;
-            if (staged) {
-              const uint32_t bar = bar0 + 8 * slot;
-              mbar_expect_tx(bar, row_bytes);
-              bulk_load_1d(ring0 + slot * static_cast<uint32_t>(a.slot_bytes), a.vectors + static_cast<int64_t>(id) * a.dim, row_bytes, bar);
+        for (;;) {
+          if (occ_mask) {
+            GS_T(tw0);
+            if (n_own <= 1) consume_slots<1>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
+            else if (n_own <= 2) consume_slots<2>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
+            else if (n_own <= 4) consume_slots<4>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
+            else consume_slots<8>(a, occ_mask, par_mask, cw, lane, staged, ring, bar0, qv, slot_id, bound, pend, &s_npend);
+            par_mask ^= occ_mask;
+            GS_T(tw1);
+            GS_ACC(3, tw0, tw1);
+          }
+          __syncwarp();  // every lane has finished reading the slots
+          bool got = false;
+          if (lane < n_own) {
+            const unsigned idx = atomicAdd(&s_head, 1u);
+            if (idx >= fifo_tail) atomicSub(&s_head, 1u);  // nothing left: hand the index back
+            else {
+              const int slot = cw + 3 * lane;
+              const int id = fifo[idx & fmask];
+              slot_id[slot] = id;
+              got = true;
+              if (staged) {
+                const uint32_t bar = bar0 + 8 * slot;
+                mbar_expect_tx(bar, row_bytes);
+                bulk_load_1d(ring0 + slot * static_cast<uint32_t>(a.slot_bytes), a.vectors + static_cast<int64_t>(id) * a.dim, row_bytes, bar);
+              }
             }
           }
+          occ_mask = __ballot_sync(kFull, got);
+          // go round again only with a full set of refills (the FIFO had at least n_own entries for this warp), a
+          // backlog behind them, and room for every slot of the ring in the pending buffer
+          if (__popc(occ_mask) < n_own) break;
+          const unsigned head_now = *reinterpret_cast<volatile unsigned*>(&s_head);
+          const int npend_now = *reinterpret_cast<volatile int*>(&s_npend);
+          if (head_now >= fifo_tail || npend_now + R > kPC) break;
         }
-        occ_mask = __ballot_sync(kFull, got);
       }
       if (!want) continue;
       GS_T(tp0);
@@ -495,7 +516,11 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
           if (w == warp) mine = total;
           total += s_wcnt[r][w];
         }
-        if (fr[r]) fifo[(fifo_tail + static_cast<uint32_t>(mine + __popc(bal[r] & lane_lt))) & fmask] = nb[r];
+        if (fr[r]) {
+          const uint32_t at = fifo_tail + static_cast<uint32_t>(mine + __popc(bal[r] & lane_lt));
+          fifo[at & fmask] = nb[r];
+          if (at < static_cast<uint32_t>(a.vlog_cap)) vlog[at] = nb[r];
+        }
       }
       fifo_tail += static_cast<uint32_t>(total);
       if (cont_mode) {
@@ -533,9 +558,18 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
     unsigned long long* out = a.out_queue + static_cast<int64_t>(q) * L;
     for (int i = tid; i < L; i += kGsThreads) out[i] = qa[i];
 #ifdef EPS_GS_PROFILE
-    if (tid == 0 && a.qtimes) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.qtimes[2 * q + 1] = t; }
+    if (tid == 0 && a.qtimes) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.qtimes[4 * q + 1] = t; a.qtimes[4 * q + 2] = st_ndist - prof_nd0; a.qtimes[4 * q + 3] = prof_iters;
+    }
 #endif
-    {
+    if (fifo_tail <= static_cast<uint32_t>(a.vlog_cap) && 10ll * (fifo_tail + L) < a.visited_words) {
+      // large table: clear only the words this query touched (the seeds and the logged fresh ids) instead of
+      // streaming zeros over the whole bitmap (1.25 MB per query at 10M rows)
+      for (int i = tid; i < L; i += kGsThreads) visited[static_cast<uint32_t>(a.init_ids[i]) >> 5] = 0u;
+      for (uint32_t i = tid; i < fifo_tail; i += kGsThreads) visited[static_cast<uint32_t>(vlog[i]) >> 5] = 0u;
+    } else {
       uint4* v4 = reinterpret_cast<uint4*>(visited);
       const int64_t n4 = a.visited_words >> 2;
       const uint4 z = make_uint4(0, 0, 0, 0);
@@ -674,7 +708,9 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   }
   const size_t smem = smem_for(R);
   const int64_t rounds = rounds_of(per_sm);
-  const int slots = static_cast<int>(std::min<int64_t>((nq + rounds - 1) / rounds, static_cast<int64_t>(per_sm) * ix->num_sms));
+  int slots = static_cast<int>(std::min<int64_t>((nq + rounds - 1) / rounds, static_cast<int64_t>(per_sm) * ix->num_sms));
+  if (ix->graph_ring_slots > 0 || ix->graph_ctas_per_sm > 0)  // tuning override: every resident slot, queries claimed dynamically
+    slots = static_cast<int>(std::min<int64_t>(nq, static_cast<int64_t>(per_sm) * ix->num_sms));
   const int64_t words = ((ix->n_indexed + 31) / 32 + 3) & ~3ll;
   if (ix->visited_slots < slots || ix->s_visited.cap < static_cast<size_t>(slots) * words * 4) {
     EPS_TRY(ix->s_visited.reserve(static_cast<size_t>(slots) * words * 4));
@@ -715,6 +751,9 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   GSArgs a;
   a.vectors = ix->d_vectors; a.offsets = ix->d_offsets; a.nbrs = ix->d_nbrs; a.ell = ix->d_ell;
   a.init_ids = ix->d_init_ids; a.seed_dist = ix->s_seed_dist.as<float>(); a.queries = d_queries;
+  constexpr int kVlogCap = 32768;
+  EPS_TRY(ix->s_vlog.reserve(static_cast<size_t>(slots) * kVlogCap * 4));
+  a.vlog = ix->s_vlog.as<int32_t>(); a.vlog_cap = kVlogCap;
   a.visited = ix->s_visited.as<uint32_t>(); a.out_queue = d_queue;
   a.work_counter = reinterpret_cast<int*>(ix->s_misc.as<unsigned char>() + 32);
   a.stats = ix->s_misc.as<unsigned long long>();
@@ -723,7 +762,7 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   a.W = width; a.exact = width == 1 ? 1 : 0; a.R = R; a.slot_bytes = slot_bytes; a.fc = fc;
   a.qtimes = nullptr;
 #ifdef EPS_GS_PROFILE
-  EPS_TRY(ix->s_tail.reserve(static_cast<size_t>(nq) * 16));  // borrowed scratch (the hybrid tail buffer is filled after the search)
+  EPS_TRY(ix->s_tail.reserve(static_cast<size_t>(nq) * 32));  // borrowed scratch (the hybrid tail buffer is filled after the search)
   a.qtimes = ix->s_tail.as<unsigned long long>();
   ix->prof_nq = nq;
 #endif
@@ -754,17 +793,36 @@ int read_graph_counters(Index* ix, eps_stats* stats) {
     for (int i = 0; i < 8; ++i) fprintf(stderr, " w%d.%s=%.1f%%", w, names[i], 100.0 * static_cast<double>(pr[8 + w * 8 + i]) / tot);
   fprintf(stderr, "\n");
   if (ix->prof_nq > 0 && ix->s_tail.p) {
-    std::vector<unsigned long long> t(static_cast<size_t>(ix->prof_nq) * 2);
+    std::vector<unsigned long long> t(static_cast<size_t>(ix->prof_nq) * 4);
     EPS_CUDA(cudaMemcpy(t.data(), ix->s_tail.p, t.size() * 8, cudaMemcpyDeviceToHost));
     unsigned long long t0 = ~0ull, t1 = 0;
-    for (int64_t q = 0; q < ix->prof_nq; ++q) { t0 = std::min(t0, t[2 * q]); t1 = std::max(t1, t[2 * q + 1]); }
+    for (int64_t q = 0; q < ix->prof_nq; ++q) { t0 = std::min(t0, t[4 * q]); t1 = std::max(t1, t[4 * q + 1]); }
     std::vector<double> end, dur;
-    for (int64_t q = 0; q < ix->prof_nq; ++q) { end.push_back((t[2 * q + 1] - t0) * 1e-3); dur.push_back((t[2 * q + 1] - t[2 * q]) * 1e-3); }
+    std::vector<std::pair<double, int64_t>> by_dur;
+    double nd_sum = 0, it_sum = 0;
+    for (int64_t q = 0; q < ix->prof_nq; ++q) {
+      end.push_back((t[4 * q + 1] - t0) * 1e-3);
+      dur.push_back((t[4 * q + 1] - t[4 * q]) * 1e-3);
+      by_dur.push_back({dur.back(), q});
+      nd_sum += static_cast<double>(t[4 * q + 2]); it_sum += static_cast<double>(t[4 * q + 3]);
+    }
     std::sort(end.begin(), end.end());
     std::sort(dur.begin(), dur.end());
+    std::sort(by_dur.begin(), by_dur.end());
     const size_t n = end.size();
     fprintf(stderr, "[gs-profile] span %.0f us; query END times (us) p10 %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f; query DURATION (us) p10 %.0f p50 %.0f p90 %.0f max %.0f\n",
             (t1 - t0) * 1e-3, end[n / 10], end[n / 2], end[n * 9 / 10], end[n * 99 / 100], end[n - 1], dur[n / 10], dur[n / 2], dur[n * 9 / 10], dur[n - 1]);
+    fprintf(stderr, "[gs-profile] per query: mean n_dist %.0f, mean iterations %.0f; slowest:", nd_sum / n, it_sum / n);
+    for (size_t i = 0; i < 6 && i < n; ++i) {
+      const int64_t q = by_dur[n - 1 - i].second;
+      fprintf(stderr, " [q%lld %.0f us n_dist %llu it %llu]", static_cast<long long>(q), by_dur[n - 1 - i].first, t[4 * q + 2], t[4 * q + 3]);
+    }
+    fprintf(stderr, "; median:");
+    for (size_t i = 0; i < 3 && i < n; ++i) {
+      const int64_t q = by_dur[n / 2 + i].second;
+      fprintf(stderr, " [q%lld %.0f us n_dist %llu it %llu]", static_cast<long long>(q), by_dur[n / 2 + i].first, t[4 * q + 2], t[4 * q + 3]);
+    }
+    fprintf(stderr, "\n");
   }
 #endif
   return EPS_OK;

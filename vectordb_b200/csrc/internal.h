@@ -78,7 +78,7 @@ struct Index {
   int num_sms = 148;
 
   // scratch
-  DevBuf s_queries, s_dist, s_topk, s_topk2, s_pass, s_filter, s_visited, s_queue, s_tail, s_out_ids, s_out_dists,
+  DevBuf s_queries, s_dist, s_topk, s_topk2, s_pass, s_filter, s_visited, s_vlog, s_queue, s_tail, s_out_ids, s_out_dists,
       s_out_counts, s_stats, s_misc, s_seed_rows, s_seed_dist, s_xnorm, s_qnorm, s_coarse, s_thr, s_cand, s_cand_cnt, s_bf16, s_qbf16, s_flags;
   int coarse_mode = 1;           // exact-scan coarse pass: 0 = fp32 SIMT only, 1 = tcgen05 TF32, 2 = tcgen05 bf16 mirror
   int coarse_guard = 1;          // verify the coarse pass after the re-score and redo unsafe queries (brute_force.cu)

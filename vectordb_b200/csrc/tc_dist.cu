@@ -34,7 +34,9 @@ constexpr int kTcABytes = kTcBM * kTcBK * 4;   // 16 KB
 constexpr int kTcBBytes = kTcBN * kTcBK * 4;   // 32 KB
 constexpr int kTcStageBytes = kTcABytes + kTcBBytes;
 constexpr int kTcThreads = 192;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
-constexpr int kTcSmem = kTcStages * kTcStageBytes + 1024 /*align*/ + 8192 /*qnorm + thresholds*/ + 256 /*barriers*/;
+constexpr int kTcStgCap = 512;   // staged survivors per epilogue warp (8-byte key + 2-byte query index each)
+constexpr int kTcStgBytes = 4 * kTcStgCap * 10 + 16;
+constexpr int kTcSmem = kTcStages * kTcStageBytes + 1024 /*align*/ + 8192 /*qnorm + thresholds*/ + 256 /*barriers*/ + kTcStgBytes;
 
 struct TcArgs {
   int64_t row_start;   // absolute first row of this chunk
@@ -57,8 +59,47 @@ struct TcArgs {
   const uint32_t* pass;         // deleted / static-filter bitmap relative to pass_base (may be null)
   int64_t pass_base;
   int cand_cap;
-  int epi_fast;  // EPS_TC_EPI=2 (read once per process): branch-light compare of the fused selection (epi_chunk_fast)
 };
+
+// Survivors of the fused selection are staged per epilogue warp in shared memory and flushed once per tile.  A push
+// straight to the per-query list needs the value its global atomicAdd returns (a ~1 us round trip under contention)
+// before the warp can go on, and while the running thresholds are still loose — the first fused launches of a scan,
+// or a clustered table where whole blobs pass — those round trips, serialised per warp, were most of the launch
+// (32 K rows took 0.7 ms, 20x their MMA time).  The flush issues four independent atomics per lane at a time,
+// after the accumulator has been handed back to the MMA warp.
+struct TcStage {
+  unsigned long long* key;  // [kTcStgCap]
+  unsigned short* q;        // [kTcStgCap]
+  int* cnt;
+};
+
+__device__ __forceinline__ void cand_push_global(const TcArgs& a, int q, unsigned long long key) {
+  const int slot = atomicAdd(&a.cand_cnt[q], 1);
+  if (slot < a.cand_cap) a.cand[static_cast<int64_t>(q) * a.cand_cap + slot] = key;
+}
+
+__device__ __forceinline__ void cand_flush(const TcArgs& a, const TcStage& st, int lane) {
+  __syncwarp();
+  const int n = min(*st.cnt, kTcStgCap);
+  for (int base = 0; base < n; base += 128) {
+    int q[4], slot[4];
+    unsigned long long key[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + 32 * u + lane;
+      q[u] = idx < n ? st.q[idx] : -1;
+      key[u] = idx < n ? st.key[idx] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) slot[u] = q[u] >= 0 ? atomicAdd(&a.cand_cnt[q[u]], 1) : a.cand_cap;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (slot[u] < a.cand_cap) a.cand[static_cast<int64_t>(q[u]) * a.cand_cap + slot[u]] = key[u];
+  }
+  __syncwarp();
+  if (lane == 0) *st.cnt = 0;
+  __syncwarp();
+}
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -127,7 +168,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // Epilogue work on one 32-column chunk of the accumulator (v[j] = dot(row, query q0+j) for this thread's row).
 __device__ __forceinline__ void epi_chunk(const TcArgs& a, const uint32_t (&v)[32], int q0, bool row_ok, float xn, int64_t i,
-                                          int64_t row_abs, const float* thr_s, const float* qn_s) {
+                                          int64_t row_abs, const float* thr_s, const float* qn_s, const TcStage& st) {
   if (a.D == nullptr) {
     // ---- fused selection: 2 instructions per element (FFMA + compare), survivors are rare ----
     if (row_ok) {
@@ -147,8 +188,10 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const uint32_t (&v)[3
               float d = tt[u];
               if (a.metric == EPS_METRIC_L2) d = fmaxf(d + qn_s[q], 0.f);
               else if (a.metric == EPS_METRIC_COSINE) d = 1.0f + d;
-              const int slot = atomicAdd(&a.cand_cnt[q], 1);
-              if (slot < a.cand_cap) a.cand[static_cast<int64_t>(q) * a.cand_cap + slot] = make_key(d, static_cast<uint32_t>(row_abs));
+              const unsigned long long key = make_key(d, static_cast<uint32_t>(row_abs));
+              const int pos = atomicAdd(st.cnt, 1);  // shared memory
+              if (pos < kTcStgCap) { st.key[pos] = key; st.q[pos] = static_cast<unsigned short>(q); }
+              else cand_push_global(a, q, key);      // stage full (flushed at the next chunk boundary)
             }
           }
         }
@@ -171,46 +214,6 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const uint32_t (&v)[3
   }
 }
 
-__device__ __forceinline__ float4 lds128(uint32_t saddr) {
-  float4 r;
-  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
-  return r;
-}
-// EPS_TC_EPI=2 (fused mode only): branch-light form of the fused
-// selection.  The thresholds of the chunk come from true LDS loads issued before the TMEM wait, all 32 compares
-// fold into four predicate chains and ONE rarely-taken branch per chunk guards the candidate push (epi_chunk
-// branches once per 4 elements behind a dependent generic load: 64 serialised round trips per 128x256 tile).
-__device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const uint32_t (&v)[32], const float4 (&ct)[8], int q0, bool row_ok,
-                                               float xn, int64_t row_abs, const float* qn_s) {
-  const float m = a.metric == EPS_METRIC_L2 ? -2.0f : -1.0f;
-  bool h0 = false, h1 = false, h2 = false, h3 = false;
-#pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    h0 |= fmaf(m, __uint_as_float(v[4 * j4 + 0]), xn) < ct[j4].x;
-    h1 |= fmaf(m, __uint_as_float(v[4 * j4 + 1]), xn) < ct[j4].y;
-    h2 |= fmaf(m, __uint_as_float(v[4 * j4 + 2]), xn) < ct[j4].z;
-    h3 |= fmaf(m, __uint_as_float(v[4 * j4 + 3]), xn) < ct[j4].w;
-  }
-  if ((h0 | h1 | h2 | h3) && row_ok) {
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      const float cc[4] = {ct[j4].x, ct[j4].y, ct[j4].z, ct[j4].w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float t = fmaf(m, __uint_as_float(v[4 * j4 + u]), xn);
-        if (t < cc[u]) {
-          const int q = q0 + 4 * j4 + u;
-          float d = t;
-          if (a.metric == EPS_METRIC_L2) d = fmaxf(d + qn_s[q], 0.f);
-          else if (a.metric == EPS_METRIC_COSINE) d = 1.0f + d;
-          const int slot = atomicAdd(&a.cand_cnt[q], 1);
-          if (slot < a.cand_cap) a.cand[static_cast<int64_t>(q) * a.cand_cap + slot] = make_key(d, static_cast<uint32_t>(row_abs));
-        }
-      }
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, TcArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + kTcStages * kTcStageBytes + 8192);
   // bars[0..3] full, [4..7] empty, [8..9] tmem_full, [10..11] tmem_empty, then the TMEM base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  unsigned char* stg = base + kTcStages * kTcStageBytes + 8192 + 256;  // [4 x keys][4 x query indices][4 counters]
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 4), tfull0 = smem_u32(bars + 8), tempty0 = smem_u32(bars + 10);
   const uint32_t stage0 = smem_u32(base);
 
@@ -307,6 +311,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
     const int lq = (warp & 3) * 32;
+    TcStage st;
+    st.key = reinterpret_cast<unsigned long long*>(stg) + (warp & 3) * kTcStgCap;
+    st.q = reinterpret_cast<unsigned short*>(stg + 4 * kTcStgCap * 8) + (warp & 3) * kTcStgCap;
+    st.cnt = reinterpret_cast<int*>(stg + 4 * kTcStgCap * 10) + (warp & 3);
+    if (lane == 0) *st.cnt = 0;
+    __syncwarp();
     uint32_t tc = 0;
     for (int rt = blockIdx.x; rt < a.n_row_tiles; rt += gridDim.x) {
       const int64_t i = static_cast<int64_t>(rt) * kTcBM + lq + lane;  // row index inside the chunk
@@ -324,30 +334,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lq) << 16) + acc * kTcBN;
         const int qbase = qt * kTcBN;
-        if (a.epi_fast && a.D == nullptr) {
-          const uint32_t thr_addr = smem_u32(thr_s);
 #pragma unroll 1
-          for (int c = 0; c < kTcBN / 32; ++c) {
-            uint32_t v[32];
-            float4 ct[8];
-            tmem_ld32(v, taddr0 + c * 32);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) ct[j4] = lds128(thr_addr + static_cast<uint32_t>(qbase + c * 32 + 4 * j4) * 4u);
-            tmem_ld_wait();
-            epi_chunk_fast(a, v, ct, qbase + c * 32, row_ok, xn, row_abs, qn_s);
-          }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < kTcBN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(v, taddr0 + c * 32);
-            tmem_ld_wait();
-            epi_chunk(a, v, qbase + c * 32, row_ok, xn, i, row_abs, thr_s, qn_s);
+        for (int c = 0; c < kTcBN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(v, taddr0 + c * 32);
+          tmem_ld_wait();
+          epi_chunk(a, v, qbase + c * 32, row_ok, xn, i, row_abs, thr_s, qn_s, st);
+          if (a.D == nullptr) {
+            __syncwarp();
+            if (*st.cnt >= kTcStgCap / 2) cand_flush(a, st, lane);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (a.D == nullptr) cand_flush(a, st, lane);  // the MMA warp already owns the accumulator again
       }
     }
   }
@@ -486,8 +487,6 @@ int tc_launch_distances(Index* ix, int64_t row_start, int64_t n, const float* d_
   }
   a.n_row_tiles = static_cast<int>((n + kTcBM - 1) / kTcBM);
   a.n_q_tiles = static_cast<int>((nq + kTcBN - 1) / kTcBN);
-  static const int env_epi = [] { const char* e = getenv("EPS_TC_EPI"); return e ? atoi(e) : 0; }();  // read once
-  a.epi_fast = env_epi == 2 ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     EPS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
