@@ -73,6 +73,8 @@ def parse():
     p.add_argument("--modes", default="graph,brute-bf16", help="candidate modes: graph, brute-bf16, brute-tf32, brute-fp32")
     p.add_argument("--L-sweep", default="128,192,256,384,512,768,1024,1536,2048,3072,4096", help="graph queue lengths, ascending; stops at the first that reaches the recall target")
     p.add_argument("--width", type=int, default=6, help="graph search width (1 = the reference's sequential order)")
+    p.add_argument("--lanes", type=int, default=2, help="concurrent batches in flight: the index + (lanes-1) read-only views, "
+                   "steps issued round-robin (1 = strictly one batch at a time)")
     p.add_argument("--ring", type=int, default=0, help="graph kernel: TMA row-ring slots per CTA (0 = auto)")
     p.add_argument("--ctas", type=int, default=0, help="graph kernel: resident CTAs per SM (0 = auto)")
     p.add_argument("--knn-k", type=int, default=64)
@@ -471,15 +473,32 @@ class Arena:
 
     def set_mode(self, m):
         a = self.a
-        if m[0] == "graph":
-            self.ix.config(m[1], m[1], force_brute=False)
-            self.ix.set_search_width(a.width)
-            self.ix.set_graph_tuning(a.ring, a.ctas)
-        else:
-            self.ix.config(512, 512, force_brute=True)
-            self.ix.set_coarse(m[2])
+        for ix in [self.ix] + [ln["ix"] for ln in getattr(self, "lanes", [])[1:]]:
+            if m[0] == "graph":
+                ix.config(m[1], m[1], force_brute=False)
+                ix.set_search_width(a.width)
+                ix.set_graph_tuning(a.ring, a.ctas)
+            else:
+                ix.config(512, 512, force_brute=True)
+                ix.set_coarse(m[2])
+
+    def open_lanes(self, n):
+        """Lane 0 = the index itself; lanes 1.. = read-only views (own stream + scratch) with their own result buffers."""
+        import torch
+        a, dev = self.a, self.dev
+        self.lanes = [{"ix": self.ix, "stream": self.stream, "ids": self.out_ids, "d": self.out_d, "c": self.out_c}]
+        for _ in range(1, n):
+            v = self.ix.view()
+            self.lanes.append({"ix": v, "stream": torch.cuda.ExternalStream(v.stream, device=dev),
+                               "ids": torch.empty_like(self.out_ids), "d": torch.empty_like(self.out_d), "c": torch.empty_like(self.out_c)})
+
+    def close_lanes(self):
+        for ln in getattr(self, "lanes", [])[1:]:
+            ln["ix"].close()
+        self.lanes = []
 
     def close(self):
+        self.close_lanes()
         self.ix.close()
         del self.X, self.Qpool
 
@@ -550,6 +569,28 @@ def main():
         barrier()
         return max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs)), stats
 
+    def timed_overlapped(m, n_steps, first):
+        """Same steps issued round-robin over the lanes without waiting for each other: one start event, one end event
+        per lane, region time = latest end - start (device clock), max over ranks."""
+        A.set_mode(m)
+        lanes = A.lanes
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(lanes[0]["stream"])
+        for ln in lanes[1:]:
+            ln["stream"].wait_event(e0)
+        for s in range(n_steps):
+            ln = lanes[s % len(lanes)]
+            q = A.Qpool[(first + s) % n_pool]
+            ln["ix"].search_device(q.data_ptr(), a.batch, a.k, ln["ids"].data_ptr(), ln["d"].data_ptr(), ln["c"].data_ptr(), sync=False)
+        ends = []
+        for ln in lanes:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(ln["stream"])
+            ends.append(e)
+        barrier()
+        return max_over_ranks(max(e0.elapsed_time(e) for e in ends))
+
     # ---- candidate modes: graph at the smallest L reaching the recall target, exact scan ----
     want = [m.strip() for m in a.modes.split(",") if m.strip()]
     report, build_s = [], None
@@ -588,31 +629,46 @@ def main():
     mode = (chosen["mode"], chosen["L"], chosen["coarse"])
 
     # ---- timed region: `value` (inputs resident in HBM) ----
+    # One batch at a time first (per-step kernel times and counters), then — graph mode, --lanes > 1 — the same steps
+    # with `lanes` batches in flight: a batch is one wave of persistent CTAs whose duration is set by its longest query
+    # (2x the median at 10M rows), so with a single batch in flight the SMs idle behind the stragglers; a second
+    # batch on a view of the index fills them.  `value` is the in-flight figure, the serial one is printed beside it.
     clocks = ClockSampler(local)
     timed_device_steps(mode, a.warmup, 0)
     clocks.start()
-    ms_dev, stats = timed_device_steps(mode, a.steps, a.warmup)
+    ms_serial, stats = timed_device_steps(mode, a.steps, a.warmup)
     have_stats = stats[0] is not None
     launches = int(sum(s["kernel_launches"] for s in stats)) if have_stats else None
-    kernel_ms = float(sum(s["kernel_ms"] for s in stats)) if have_stats else ms_dev
+    kernel_ms = float(sum(s["kernel_ms"] for s in stats)) if have_stats else ms_serial
     agg = {k: float(sum(s[k] for s in stats)) if have_stats else 0.0 for k in ("n_dist", "n_seed", "n_expand", "n_edges")}
+    ms_dev, n_lanes, lanes_recall = ms_serial, 1, None
+    if mode[0] == "graph" and a.lanes > 1 and group is None:
+        A.open_lanes(a.lanes)
+        A.set_mode(mode)
+        for ln in A.lanes:  # every lane answers the ground-truth batch like the index itself
+            ln["ix"].search_device(A.Qpool[0].data_ptr(), a.batch, a.k, ln["ids"].data_ptr(), ln["d"].data_ptr(), ln["c"].data_ptr())
+        lanes_recall = [recall_of(A.truth, ln["ids"], a.k) for ln in A.lanes]
+        timed_overlapped(mode, max(a.warmup, len(A.lanes)), 0)
+        ms_dev = timed_overlapped(mode, a.steps, a.warmup)
+        n_lanes = len(A.lanes)
+        kernel_ms = ms_dev  # region time: the launches of different lanes overlap, per-launch times do not add up
 
     # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region ----
     import ctypes as C
     from vectordb_b200.lib import check
     A.set_mode(mode)
     Qhost = [torch.empty((a.batch, a.dim), dtype=torch.float32).pin_memory().copy_(q.cpu()) for q in A.Qpool]
-    e_ids = np.empty((a.batch, a.k), np.int64)
-    e_d = np.empty((a.batch, a.k), np.float64)
-    e_c = np.empty(a.batch, np.int64)
+    e_out = [(np.empty((a.batch, a.k), np.int64), np.empty((a.batch, a.k), np.float64), np.empty(a.batch, np.int64)) for _ in range(n_lanes)]
     h_ids = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
     h_d = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
     d_q = torch.empty((a.batch, a.dim), dtype=torch.float32, device=dev)
 
-    def e2e_step(s):
+    def e2e_step(s, lane=0):
         q = Qhost[s % n_pool]
         if group is None:
-            check(ix.L.eps_search_batch(ix.h, C.c_void_p(q.data_ptr()), a.batch, a.k, None, 0, e_ids.ctypes.data_as(C.c_void_p),
+            h = A.lanes[lane]["ix"].h if n_lanes > 1 else ix.h
+            e_ids, e_d, e_c = e_out[lane]
+            check(ix.L.eps_search_batch(h, C.c_void_p(q.data_ptr()), a.batch, a.k, None, 0, e_ids.ctypes.data_as(C.c_void_p),
                                         e_d.ctypes.data_as(C.c_void_p), e_c.ctypes.data_as(C.c_void_p), None))
         else:  # row shards: H2D of the replicated batch, sharded search + exchange, D2H of the merged result
             with torch.cuda.stream(A.stream):
@@ -622,14 +678,35 @@ def main():
                 h_d.copy_(m_d, non_blocking=True)
             A.stream.synchronize()
 
-    for s in range(a.warmup):
-        e2e_step(s)
+    def e2e_run(first, n_steps):
+        """n_steps calls of the blocking host-buffer entry point; with lanes, one caller thread per lane (the call
+        releases the GIL), steps dealt round-robin."""
+        if n_lanes == 1:
+            for s in range(n_steps):
+                e2e_step(first + s)
+            return
+        errs = []
+
+        def worker(li):
+            try:
+                for s in range(li, n_steps, n_lanes):
+                    e2e_step(first + s, li)
+            except Exception as e:  # surfaced below
+                errs.append(e)
+        ts = [threading.Thread(target=worker, args=(li,)) for li in range(n_lanes)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    e2e_run(0, max(a.warmup, n_lanes))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(A.stream)
-    for s in range(a.steps):
-        e2e_step(a.warmup + s)
-    e1.record(A.stream)
+    e2e_run(a.warmup, a.steps)
+    e1.record(A.stream)  # every call has synchronised its own lane before returning
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop()
@@ -700,11 +777,16 @@ def main():
             "exact scan (tcgen05 %s coarse pass + fp32 re-score)" % mode[2],
             "row shards + in-library ncclAllGather + merge" if a.shard_rows else "replicated table, query stream partitioned over ranks")),
             key_rec: chosen[key_rec], "l2_flush": "inputs (%.1f GB table) larger than L2" % (rows * a.dim * 4 / 1e9),
-            "fp64_groundtruth_check": chk},
+            "fp64_groundtruth_check": chk, "batches_in_flight": n_lanes},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.dim * 4,
                 "d2h_bytes_per_step": a.batch * a.k * 12 + (0 if group is not None else a.batch * 8)},
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "modes": report,
     }
+    if n_lanes > 1:
+        out["one_batch_at_a_time"] = {"value": units / (ms_serial / 1000.0), "unit": "queries/s", "ms_per_step": ms_serial / a.steps,
+                                      "roofline_frac": roof["achieved"] * ms_dev / ms_serial / roof["peak"]}
+        out["config"]["recall_per_lane"] = lanes_recall
+        roof["timing"] = "%d steps over %d lanes (index + views); achieved = algorithmic bytes of the steps / region time" % (a.steps, n_lanes)
     out.update(extra)
     if misses is not None:
         out["exact_scan_misses_vs_fp32"] = misses
@@ -782,6 +864,14 @@ def main():
                 ag = {k: float(sum(x[k] for x in st)) for k in ("n_dist", "n_seed", "n_expand", "n_edges")}
                 trep["graph"] = {"value": a.batch * len(st) / (ms / 1000.0), "unit": "queries/s", "L": gm[1], "width": a.width,
                                  key_rec: grec, "roofline": graph_roofline(ag, gm[1], k_ms, len(st)), "L_sweep": sweep}
+                if a.lanes > 1:  # the same steps with `lanes` batches in flight (see the headline record)
+                    A.open_lanes(a.lanes)
+                    timed_overlapped(gm, max(a.warmup, a.lanes), 0)
+                    ms_o = timed_overlapped(gm, len(st), a.warmup)
+                    trep["graph"] = {"value": a.batch * len(st) / (ms_o / 1000.0), "unit": "queries/s", "L": gm[1], "width": a.width,
+                                     key_rec: grec, "batches_in_flight": a.lanes, "roofline": graph_roofline(ag, gm[1], ms_o, len(st)),
+                                     "one_batch_at_a_time": trep["graph"], "L_sweep": sweep}
+                    A.close_lanes()
             m = ("brute", 0, "bf16")
             A.set_mode(m)
             A.search(A.Qpool[0])

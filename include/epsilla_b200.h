@@ -106,6 +106,15 @@ EPS_API int eps_index_create(eps_index** out, int metric, int64_t dim, const flo
                      int device);
 EPS_API void eps_index_destroy(eps_index* ix);
 
+/* A read-only VIEW of an index for concurrent searches: the view shares the base's device table, graph, deleted bits
+ * and attribute mirrors and has its own stream and scratch, so batches submitted to the base and to its views (from
+ * different host threads, or with sync = 0) overlap on the device — the engine's analogue is the pool of
+ * NumExecutorPerField executors over one field (db/execution/executor_pool.hpp, config.hpp:17).  The executor
+ * parameters (eps_index_config, width, coarse mode) are copied at creation and may then be set per view.  While an
+ * index has live views every call that would modify it (rows, graph, deleted bits, attributes, build) fails with
+ * EPS_ERR_INVALID_ARGUMENT, and so does the same call on a view.  Destroy the views before the base. */
+EPS_API int eps_index_create_view(eps_index* base, eps_index** out);
+
 /* Mirror rows [uploaded, n_rows_now) to HBM; n_rows_now = record_number_ snapshot
  * (db/execution/vec_search_executor.cpp:839). */
 EPS_API int eps_index_sync_rows(eps_index* ix, int64_t n_rows_now);

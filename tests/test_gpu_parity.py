@@ -668,3 +668,43 @@ def test_exact_scan_guard_catches_a_coarse_pass_that_cannot_rank(vdb):
     got, _, _, st = ix.search(Q2, k)
     assert st["n_redone"] == 0 and (got == want).mean() > 0.999
     ix.close()
+
+
+def test_views_search_concurrently_and_freeze_the_base(vdb):
+    """eps_index_create_view: a view answers exactly like its base (exact mode, width 1), batches issued to the base and
+    to the view without synchronisation overlap and still give the same answers, and the base refuses modifications
+    while the view lives."""
+    import torch
+    rng = np.random.default_rng(11)
+    n, dim, nq, k = 6000, 64, 256, 10
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    Q = rng.standard_normal((nq, dim)).astype(np.float32)
+    ix = vdb.Index("l2", dim, host_vectors=X)
+    ix.sync_rows(n)
+    ix.build(n, knn_k=32, out_degree=24)
+    ix.config(64, 64)
+    ix.set_search_width(1)
+    want_ids, want_d, want_c, _ = ix.search(Q, k)
+    v = ix.view()
+    got_ids, got_d, got_c, _ = v.search(Q, k)
+    assert np.array_equal(want_ids, got_ids) and np.array_equal(want_c, got_c) and np.allclose(want_d, got_d, rtol=1e-6)
+    # asynchronous, interleaved batches on the two handles
+    dev = torch.device("cuda", 0)
+    dq = torch.from_numpy(Q).to(dev)
+    outs = []
+    for h in (ix, v, ix, v):
+        oi = torch.empty((nq, k), dtype=torch.int64, device=dev); od = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        oc = torch.empty((nq,), dtype=torch.int64, device=dev)
+        h.search_device(dq.data_ptr(), nq, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), sync=False)
+        outs.append((h, oi))
+    for h, oi in outs:
+        torch.cuda.ExternalStream(h.stream, device=dev).synchronize()
+        assert np.array_equal(oi.cpu().numpy(), want_ids)
+    # frozen base, read-only view
+    for call in (lambda: ix.sync_rows(n), lambda: ix.build(n), lambda: ix.set_deleted(np.zeros(n // 8 + 1, np.uint8)),
+                 lambda: v.set_deleted(np.zeros(n // 8 + 1, np.uint8)), lambda: v.build(n)):
+        with pytest.raises(vdb.EpsError):
+            call()
+    v.close()
+    ix.set_deleted(np.zeros(n // 8 + 1, np.uint8))  # thawed
+    ix.close()

@@ -299,11 +299,16 @@ void eps_index_destroy(eps_index* h) {
   Index* ix = reinterpret_cast<Index*>(h);
   cudaSetDevice(ix->device);
   cudaStreamSynchronize(ix->stream);
-  eps::free_graph(ix);
-  if (ix->owns_vectors && ix->d_vectors) cudaFree(ix->d_vectors);
-  if (ix->d_deleted) cudaFree(ix->d_deleted);
-  if (ix->d_attrs) cudaFree(ix->d_attrs);
-  for (auto& sc : ix->str_cols) if (sc.d_codes) cudaFree(sc.d_codes);
+  if (ix->view_of) {  // a view owns its seed set, stream and scratch only
+    if (ix->d_init_ids) cudaFree(ix->d_init_ids);
+    --ix->view_of->n_views;
+  } else {
+    eps::free_graph(ix);
+    if (ix->owns_vectors && ix->d_vectors) cudaFree(ix->d_vectors);
+    if (ix->d_deleted) cudaFree(ix->d_deleted);
+    if (ix->d_attrs) cudaFree(ix->d_attrs);
+    for (auto& sc : ix->str_cols) if (sc.d_codes) cudaFree(sc.d_codes);
+  }
   eps::DevBuf* bufs[] = {&ix->s_queries, &ix->s_dist, &ix->s_topk, &ix->s_topk2, &ix->s_pass, &ix->s_filter,
                          &ix->s_visited, &ix->s_vlog, &ix->s_queue, &ix->s_tail, &ix->s_out_ids, &ix->s_out_dists,
                          &ix->s_out_counts, &ix->s_stats, &ix->s_misc, &ix->s_seed_rows, &ix->s_seed_dist, &ix->s_xnorm, &ix->s_qnorm, &ix->s_coarse, &ix->s_thr, &ix->s_cand, &ix->s_cand_cnt, &ix->s_bf16, &ix->s_qbf16, &ix->s_flags};
@@ -314,10 +319,54 @@ void eps_index_destroy(eps_index* h) {
   delete ix;
 }
 
+// A read-only view of an index: the same device table, graph and segment mirrors, its own stream and scratch.
+// Searches on a view and on its base (or on several views) run concurrently — the tail of one batch, where a few
+// long queries hold their SMs alone, overlaps the head of the next.  The base refuses to be modified while it has views.
+int eps_index_create_view(eps_index* base_h, eps_index** out) {
+  if (!out) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  Index* base = reinterpret_cast<Index*>(base_h);
+  if (!base) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
+  if (base->view_of) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "a view cannot be the base of another view");
+  EPS_TRY(eps::check_device(base->device));
+  EPS_TRY(eps::ensure_ell(base, nullptr));
+  EPS_CUDA(cudaStreamSynchronize(base->stream));  // uploads, graph install and the adjacency table are complete
+  Index* ix = new Index();
+  ix->view_of = base;
+  ix->device = base->device; ix->metric = base->metric; ix->dim = base->dim; ix->capacity = base->capacity;
+  ix->host_vectors = nullptr; ix->d_vectors = base->d_vectors; ix->owns_vectors = false; ix->n_rows = base->n_rows;
+  ix->vec4 = base->vec4;
+  ix->n_indexed = base->n_indexed; ix->n_edges = base->n_edges; ix->nav = base->nav;
+  ix->d_offsets = base->d_offsets; ix->d_nbrs = base->d_nbrs; ix->d_ell = base->d_ell;
+  ix->d_deleted = base->d_deleted; ix->deleted_bytes = base->deleted_bytes; ix->deleted_cap = base->deleted_cap;
+  ix->any_deleted = base->any_deleted;
+  ix->d_attrs = base->d_attrs; ix->attr_stride = base->attr_stride; ix->attr_rows = base->attr_rows;
+  ix->attr_cap_rows = base->attr_cap_rows;
+  for (int i = 0; i < eps::kMaxStringCols; ++i) ix->str_cols[i] = base->str_cols[i];
+  ix->L_master = base->L_master; ix->L_local = base->L_local; ix->prefilter = base->prefilter; ix->force_brute = base->force_brute;
+  ix->search_width = base->search_width; ix->graph_ring_slots = base->graph_ring_slots;
+  ix->graph_ctas_per_sm = base->graph_ctas_per_sm; ix->num_sms = base->num_sms;
+  ix->coarse_mode = base->coarse_mode; ix->coarse_guard = base->coarse_guard; ix->coarse_boost = base->coarse_boost;
+  cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete ix; return eps::fail(EPS_ERR_CUDA, cudaGetErrorString(e)); }
+  for (auto& ev : ix->ev) cudaEventCreate(&ev);
+  ++base->n_views;
+  *out = reinterpret_cast<eps_index*>(ix);
+  return EPS_OK;
+}
+
+// table, graph and segment mirrors of a view belong to its base; a base with live views is frozen
+static int check_mutable(const Index* ix) {
+  if (ix->view_of) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "a view is read-only");
+  if (ix->n_views > 0) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "the index has live views: destroy them before modifying it");
+  return EPS_OK;
+}
+
 int eps_index_sync_rows(eps_index* h, int64_t n_rows_now) {
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
   EPS_TRY(eps::check_device(ix->device));
+  EPS_TRY(check_mutable(ix));
   if (!ix->owns_vectors) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "index has no host vector table to mirror");
   if (n_rows_now < ix->n_rows || n_rows_now > ix->capacity)
     return eps::fail(EPS_ERR_INVALID_ARGUMENT, "n_rows_now outside [mirrored rows, capacity]");
@@ -335,6 +384,7 @@ int eps_index_adopt_device_rows(eps_index* h, const float* d_vectors, int64_t n_
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix || !d_vectors) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null argument");
   EPS_TRY(eps::check_device(ix->device));
+  EPS_TRY(check_mutable(ix));
   if (n_rows < 0 || n_rows >= (1ll << 31)) return eps::fail(EPS_ERR_UNSUPPORTED, "row count must be in [0, 2^31): keys carry 31-bit ids");
   if (ix->owns_vectors && ix->d_vectors) cudaFree(ix->d_vectors);
   ix->owns_vectors = false;
@@ -354,6 +404,7 @@ int eps_index_set_graph(eps_index* h, int64_t n_indexed, const int64_t* offsets,
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
   EPS_TRY(eps::check_device(ix->device));
+  EPS_TRY(check_mutable(ix));
   eps::free_graph(ix);
   if (n_indexed <= 0) return EPS_OK;
   if (!offsets) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null offset table");
@@ -398,6 +449,7 @@ int eps_index_build(eps_index* h, int64_t n, const eps_build_params* params) {
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
   EPS_TRY(eps::check_device(ix->device));
+  EPS_TRY(check_mutable(ix));
   return eps::build_graph(ix, n, params);
 }
 
@@ -426,6 +478,7 @@ int eps_index_set_deleted(eps_index* h, const uint8_t* bitset, int64_t nbytes) {
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
   EPS_TRY(eps::check_device(ix->device));
+  EPS_TRY(check_mutable(ix));
   if (!bitset || nbytes <= 0) { ix->any_deleted = false; ix->deleted_bytes = 0; ix->h_deleted.clear(); return EPS_OK; }
   int64_t lo = 0, hi = nbytes;  // dirty span [lo, hi)
   const bool same_geometry = ix->d_deleted && static_cast<int64_t>(ix->h_deleted.size()) == nbytes && nbytes <= ix->deleted_cap;
@@ -469,6 +522,7 @@ int eps_index_set_attrs(eps_index* h, const char* table, int64_t stride, int64_t
   Index* ix = reinterpret_cast<Index*>(h);
   if (!ix) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "null index");
   EPS_TRY(eps::check_device(ix->device));
+  EPS_TRY(check_mutable(ix));
   if (!table || stride <= 0 || n_rows <= 0) {
     if (ix->d_attrs) { cudaFree(ix->d_attrs); ix->d_attrs = nullptr; }
     ix->attr_stride = stride; ix->attr_rows = 0; ix->attr_cap_rows = 0; ix->attr_src = nullptr;
@@ -502,6 +556,7 @@ int eps_index_set_string_codes(eps_index* h, int column, int64_t first_row, cons
   if (column < 0 || column >= eps::kMaxStringCols) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "string column index must be in [0, 8)");
   if (first_row < 0 || count < 0 || (count > 0 && !codes)) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "bad row range / null codes");
   EPS_TRY(eps::check_device(ix->device));
+  EPS_TRY(check_mutable(ix));
   eps::StrCol& sc = ix->str_cols[column];
   if (first_row > sc.rows) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "string codes must be appended without gaps");
   const int64_t need = first_row + count;

@@ -662,6 +662,16 @@ static int ring_slots_for(const Index* ix, int slot_bytes) {
   return std::max(2, std::min(r, kMaxR));
 }
 
+int ensure_ell(Index* ix, uint64_t* launches) {
+  if (ix->d_ell || !ix->d_offsets) return EPS_OK;
+  EPS_CUDA(cudaMalloc(&ix->d_ell, static_cast<size_t>(ix->n_indexed) * kEll * 4));
+  const int64_t tot = ix->n_indexed * kEll;
+  csr_to_ell_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(ix->d_offsets, ix->d_nbrs, ix->n_indexed, ix->d_ell);
+  EPS_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return EPS_OK;
+}
+
 int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsigned long long* d_queue,
                  eps_stats* stats) {
   if (L < 1 || L > ix->n_indexed) return fail(EPS_ERR_INVALID_ARGUMENT, "graph_search: L out of range");
@@ -727,14 +737,7 @@ int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsig
   EPS_TRY(ix->s_misc.reserve(256));  // [0..3] counters, [+32 B] work counter, [8..24] developer phase timers
   EPS_CUDA(cudaMemsetAsync(ix->s_misc.p, 0, 256, ix->stream));
   uint64_t launches = 1;
-  if (!ix->d_ell) {  // fixed-stride adjacency, built once per installed graph
-    EPS_CUDA(cudaMalloc(&ix->d_ell, static_cast<size_t>(ix->n_indexed) * kEll * 4));
-    const int64_t tot = ix->n_indexed * kEll;
-    csr_to_ell_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ix->stream>>>(ix->d_offsets, ix->d_nbrs,
-                                                                                        ix->n_indexed, ix->d_ell);
-    EPS_CUDA(cudaGetLastError());
-    ++launches;
-  }
+  EPS_TRY(ensure_ell(ix, &launches));
   if (ix->seed_rows_L != L) {  // contiguous copy of the query-independent seed rows
     EPS_TRY(ix->s_seed_rows.reserve(static_cast<size_t>(L) * ix->dim * 4));
     const int64_t tot = L * ix->dim;

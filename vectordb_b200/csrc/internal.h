@@ -38,6 +38,8 @@ struct Index {
   const float* host_vectors = nullptr;
   float* d_vectors = nullptr;   // [capacity x dim] (owned unless adopted)
   bool owns_vectors = false;
+  Index* view_of = nullptr;     // read-only view (eps_index_create_view): table, graph, segment mirrors belong to this index
+  int n_views = 0;              // live views of this index; mutating entry points refuse while > 0
   int64_t n_rows = 0;           // rows mirrored so far (record_number_ snapshot)
   bool vec4 = false;            // dim % 4 == 0 and 16-B aligned base
 
@@ -133,6 +135,7 @@ int brute_force_knn_rows(Index* ix, int64_t q_start, int64_t nq, int64_t n_rows,
 int graph_search(Index* ix, const float* d_queries, int64_t nq, int64_t L, unsigned long long* d_queue,
                  eps_stats* stats);
 int prepare_init_ids(Index* ix, int64_t L);
+int ensure_ell(Index* ix, uint64_t* launches);  // fixed-stride adjacency of the installed graph (built once)
 // out[i] = row d_ids[i] of the table (contiguous copy; used for seed rows and for the build's repair searches)
 int gather_rows(Index* ix, const int32_t* d_ids, int64_t n, float* d_out);
 int read_graph_counters(Index* ix, eps_stats* stats);

@@ -53,6 +53,17 @@ class Index:
         self.h = h
         self._keep = []
 
+    def view(self):
+        """Read-only view sharing this index's device data, with its own stream and scratch (eps_index_create_view):
+        searches on the view overlap searches on the base.  Close the views before the base."""
+        v = Index.__new__(Index)
+        v.L, v.metric, v.dim, v.device, v._host, v.capacity, v._keep = self.L, self.metric, self.dim, self.device, None, self.capacity, []
+        h = C.c_void_p()
+        check(self.L.eps_index_create_view(self.h, C.byref(h)))
+        v.h = h
+        v._base = self  # keeps the base alive
+        return v
+
     def close(self):
         if getattr(self, "h", None):
             self.L.eps_index_destroy(self.h)

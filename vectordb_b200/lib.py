@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 EXPORTS = [
-    "eps_index_create", "eps_index_destroy", "eps_index_sync_rows", "eps_index_adopt_device_rows", "eps_index_device_rows", "eps_index_rows",
+    "eps_index_create", "eps_index_destroy", "eps_index_create_view", "eps_index_sync_rows", "eps_index_adopt_device_rows", "eps_index_device_rows", "eps_index_rows",
     "eps_index_set_graph", "eps_index_build", "eps_index_get_graph", "eps_index_set_deleted", "eps_index_set_attrs", "eps_index_set_string_codes",
     "eps_index_config", "eps_index_set_coarse", "eps_index_set_coarse_guard", "eps_index_set_search_width", "eps_index_set_graph_tuning", "eps_search_batch", "eps_search_batch_device", "eps_merge_shards_device", "eps_facet_batch", "eps_shard_unique_id", "eps_shard_group_create", "eps_shard_group_destroy", "eps_search_batch_sharded", "eps_normalize",
     "eps_pair_distances", "eps_index_stream", "eps_last_error", "eps_version", "eps_device_count",
@@ -68,6 +68,7 @@ def load_library():
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
     L.eps_index_create.argtypes = [C.POINTER(vp), i32, i64, vp, i64, i32]
     L.eps_index_destroy.argtypes = [vp]
+    L.eps_index_create_view.argtypes = [vp, C.POINTER(vp)]
     L.eps_index_destroy.restype = None
     L.eps_index_sync_rows.argtypes = [vp, i64]
     L.eps_index_adopt_device_rows.argtypes = [vp, vp, i64]
