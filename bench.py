@@ -636,7 +636,12 @@ def main():
     clocks = ClockSampler(local)
     timed_device_steps(mode, a.warmup, 0)
     clocks.start()
+    prof_region = bool(os.environ.get("EPS_BENCH_PROFILE_REGION"))  # ncu --profile-from-start off: only these steps are captured
+    if prof_region:
+        torch.cuda.profiler.start()
     ms_serial, stats = timed_device_steps(mode, a.steps, a.warmup)
+    if prof_region:
+        torch.cuda.profiler.stop()
     have_stats = stats[0] is not None
     launches = int(sum(s["kernel_launches"] for s in stats)) if have_stats else None
     kernel_ms = float(sum(s["kernel_ms"] for s in stats)) if have_stats else ms_serial
