@@ -73,7 +73,7 @@ def parse():
     p.add_argument("--modes", default="graph,brute-bf16", help="candidate modes: graph, brute-bf16, brute-tf32, brute-fp32")
     p.add_argument("--L-sweep", default="128,192,256,384,512,768,1024,1536,2048,3072,4096", help="graph queue lengths, ascending; stops at the first that reaches the recall target")
     p.add_argument("--width", type=int, default=6, help="graph search width (1 = the reference's sequential order)")
-    p.add_argument("--lanes", type=int, default=2, help="concurrent batches in flight: the index + (lanes-1) read-only views, "
+    p.add_argument("--lanes", type=int, default=3, help="concurrent batches in flight: the index + (lanes-1) read-only views, "
                    "steps issued round-robin (1 = strictly one batch at a time)")
     p.add_argument("--ring", type=int, default=0, help="graph kernel: TMA row-ring slots per CTA (0 = auto)")
     p.add_argument("--ctas", type=int, default=0, help="graph kernel: resident CTAs per SM (0 = auto)")
@@ -747,6 +747,15 @@ def main():
                 "hbm_algorithmic_GBps": bytes_alg / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0}
 
     roof = graph_roofline(agg, mode[1], kernel_ms, a.steps) if mode[0] == "graph" else scan_roofline(mode[2], kernel_ms, a.steps)
+    if mode[0] == "graph":  # measured DRAM traffic of this exact workload, when an ncu capture of it is committed
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_measured_traffic.json")) as f:
+                for e in json.load(f)["entries"]:
+                    if (e["rows"], e["dim"], e["dist"], e["batch"], e["L"], e["width"]) == (a.rows, a.dim, a.dist, a.batch, mode[1], a.width):
+                        roof["traffic"] = e["bytes_per_launch"]
+                        roof["traffic_source"] = e["source"]
+        except (OSError, ValueError, KeyError):
+            pass
 
     # ---- secondary records of the non-chosen modes, each with its own roofline ----
     extra = {}

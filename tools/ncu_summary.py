@@ -2,7 +2,8 @@
 profiles/: duration, DRAM / L2 / shared traffic, pipe utilisation, occupancy, registers, stall reasons per issue, and
 the source lines with the most stall samples.  Runs where ncu is installed (no GPU needed).
 
-  python tools/ncu_summary.py gpurun_out/x.ncu-rep "title" [algorithmic_bytes] > profiles/r02_ncu_x.md
+  python tools/ncu_summary.py gpurun_out/x.ncu-rep "title" [algorithmic_bytes] [kernel-name regex] > profiles/r02_ncu_x.md
+(with a kernel-name regex, the first matching launch of a multi-kernel report is summarised)
 """
 import csv
 import io
@@ -10,14 +11,19 @@ import subprocess
 import sys
 
 
+KFILTER = []
+
+
 def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"] + KFILTER, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
 def main():
     rep, title = sys.argv[1], sys.argv[2]
-    alg = float(sys.argv[3]) if len(sys.argv) > 3 else None
+    alg = float(sys.argv[3]) if len(sys.argv) > 3 and float(sys.argv[3]) > 0 else None
+    if len(sys.argv) > 4:
+        KFILTER.extend(["-k", "regex:" + sys.argv[4], "-c", "1"])
     rows = page(rep, "raw")
     hdr, units, vals = rows[0], rows[1], rows[2]
     m = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
