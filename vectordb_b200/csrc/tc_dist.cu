@@ -65,8 +65,8 @@ struct TcArgs {
 // straight to the per-query list needs the value its global atomicAdd returns (a ~1 us round trip under contention)
 // before the warp can go on, and while the running thresholds are still loose — the first fused launches of a scan,
 // or a clustered table where whole blobs pass — those round trips, serialised per warp, were most of the launch
-// (32 K rows took 0.7 ms, 20x their MMA time).  The flush issues four independent atomics per lane at a time,
-// after the accumulator has been handed back to the MMA warp.
+// (32 K rows took 0.7 ms, 20x their MMA time).  The stage is flushed when half full and at the end of the CTA's tiles,
+// four independent global atomics per lane at a time.
 struct TcStage {
   unsigned long long* key;  // [kTcStgCap]
   unsigned short* q;        // [kTcStgCap]
@@ -348,9 +348,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dist_kernel(const __grid_con
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-        if (a.D == nullptr) cand_flush(a, st, lane);  // the MMA warp already owns the accumulator again
       }
     }
+    if (a.D == nullptr) cand_flush(a, st, lane);  // what is left in the stage (it is also flushed whenever half full)
   }
   __syncthreads();
   if (warp == 1) {
