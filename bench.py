@@ -642,8 +642,14 @@ def main():
     ms_serial, stats = timed_device_steps(mode, a.steps, a.warmup)
     if prof_region:
         torch.cuda.profiler.stop()
+    if stats[0] is None:  # row shards: the sharded call returns no counters; the local search of the same steps does
+        stats = [A.search(A.Qpool[(a.warmup + s_) % n_pool], want_stats=True) for s_ in range(a.steps)]
+        for st_ in stats:
+            st_["kernel_ms"] = ms_serial / a.steps  # step time of the sharded call (local search + exchange + merge)
     have_stats = stats[0] is not None
     launches = int(sum(s["kernel_launches"] for s in stats)) if have_stats else None
+    if launches is not None and group is not None:
+        launches += 2 * a.steps  # pack_shard_block_kernel + merge_shards_kernel around the ncclAllGather
     kernel_ms = float(sum(s["kernel_ms"] for s in stats)) if have_stats else ms_serial
     agg = {k: float(sum(s[k] for s in stats)) if have_stats else 0.0 for k in ("n_dist", "n_seed", "n_expand", "n_edges")}
     ms_dev, n_lanes, lanes_recall = ms_serial, 1, None
