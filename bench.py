@@ -8,10 +8,14 @@ roofline fraction of the dominant kernel and with the reference's own CPU path t
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload.  Three synthetic 10M x 768 tables (random floats, seeded, generated on the device):
-  * "manifold" (headline, --dist): 1024 overlapping unit Gaussians in a 32-d latent space, mapped into R^768 by a
-    fixed orthonormal map, plus isotropic noise — clustered data of low intrinsic dimension, the structure embedding
-    tables have and the case a graph index exists for (queue length L of a few hundred reaches recall 0.99);
-  * "cluster": SURVEY.md §8d's clustered table, 1024 centres with ISOTROPIC sigma = 0.1 blobs in all 768 dimensions.
+  * "manifold" (headline, --dist): SURVEY.md §8d's clustered variant — 1024 Gaussian centres, sigma = 0.1, seed 44 —
+    with the blobs living in a 32-d latent space (centres N(0, 0.15^2) there, so neighbouring blobs overlap) that a
+    fixed orthonormal map embeds in R^768, plus isotropic noise of sigma 0.005: clustered data of low intrinsic
+    dimension, the structure embedding tables have and the case a graph index exists for (a queue length L of a
+    few hundred reaches recall 0.99).  (Logs made before this scaling describe the same table with unit blobs: every
+    length is 10x larger, every ranking identical.)
+  * "cluster": the same variant read the other way, centres uniform in the unit cube with ISOTROPIC sigma = 0.1 blobs in
+    all 768 dimensions.
     Distances inside a blob concentrate, so recall 0.99 means visiting the query's whole 9.8k-row blob, and the 1024
     blobs are separate graph components that the search can only enter through the navigation point's > 1000
     out-neighbours: L >= 1536 (PrepareInitIds seeds exactly L of them).  Graph search still beats the exact scan;
@@ -100,9 +104,10 @@ def parse():
 # a seeded Philox stream; the CPU generator of the same seed is a different stream and is only used when no GPU
 # is present, i.e. in the CPU contract test)
 # ------------------------------------------------------------------------------------------------------
-LATENT_DIM = int(os.environ.get("EPS_BENCH_LATENT", "32"))      # "manifold" tables: dimension of the latent space
-LATENT_SPREAD = float(os.environ.get("EPS_BENCH_SPREAD", "1.5"))  # std of the mixture centres, in units of the blob std
-LATENT_NOISE = float(os.environ.get("EPS_BENCH_NOISE", "0.05"))   # isotropic noise added in the full space
+LATENT_DIM = int(os.environ.get("EPS_BENCH_LATENT", "32"))       # "manifold" tables: dimension of the latent space
+LATENT_SIGMA = float(os.environ.get("EPS_BENCH_SIGMA", "0.1"))     # std of every Gaussian blob (sigma = 0.1)
+LATENT_SPREAD = float(os.environ.get("EPS_BENCH_SPREAD", "1.5"))   # std of the mixture centres, in units of the blob std
+LATENT_NOISE = float(os.environ.get("EPS_BENCH_NOISE", "0.05"))    # isotropic noise in the full space, in units of the blob std
 
 
 def _mixture(dim, dist, device, centers_n):
@@ -115,7 +120,7 @@ def _mixture(dim, dist, device, centers_n):
     gc.manual_seed(44)
     if dist == "cluster":
         return torch.rand((centers_n, dim), generator=gc, device=device), None
-    lat = torch.randn((centers_n, LATENT_DIM), generator=gc, device=device) * LATENT_SPREAD
+    lat = torch.randn((centers_n, LATENT_DIM), generator=gc, device=device) * (LATENT_SPREAD * LATENT_SIGMA)
     a = torch.randn((dim, LATENT_DIM), generator=gc, device=device)
     q, _ = torch.linalg.qr(a)  # dim x LATENT_DIM, orthonormal columns
     return lat, q.T.contiguous()
@@ -132,9 +137,9 @@ def _draw(out, dist, g, device, centers, umap):
         out.normal_(0.0, 0.1, generator=g)
         out += centers[lab]
         return
-    z = torch.randn((n, LATENT_DIM), generator=g, device=device)
+    z = torch.randn((n, LATENT_DIM), generator=g, device=device) * LATENT_SIGMA
     z += centers[lab]
-    out.normal_(0.0, LATENT_NOISE, generator=g)
+    out.normal_(0.0, LATENT_NOISE * LATENT_SIGMA, generator=g)
     out.addmm_(z, umap)
 
 
@@ -223,9 +228,9 @@ def measured_peaks():
 def workload_name(a, extra=""):
     data = {"uniform": "iid-uniform[0,1)",
             "cluster": "clustered, isotropic (%d Gaussian centres in the unit cube, sigma=0.1 in all %d dimensions)" % (a.centers, a.dim),
-            "manifold": "clustered, low intrinsic dimension (%d unit Gaussians, centre std %.1f, in a %d-d latent space mapped "
-                        "to R^%d by a fixed orthonormal map, + isotropic noise sigma=%.2f)" % (
-                            a.centers, LATENT_SPREAD, LATENT_DIM, a.dim, LATENT_NOISE)}[a.dist]
+            "manifold": "clustered, low intrinsic dimension (%d Gaussian centres, sigma=%.2f, centre std %.3f, in a %d-d latent "
+                        "space mapped to R^%d by a fixed orthonormal map, + isotropic noise sigma=%.4f)" % (
+                            a.centers, LATENT_SIGMA, LATENT_SPREAD * LATENT_SIGMA, LATENT_DIM, a.dim, LATENT_NOISE * LATENT_SIGMA)}[a.dist]
     return "%dx%d f32 %s %s (seed 42), batch=%d, top-%d%s" % (a.rows, a.dim, a.metric, data, a.batch, a.k, extra)
 
 
