@@ -707,4 +707,9 @@ def test_views_search_concurrently_and_freeze_the_base(vdb):
             call()
     v.close()
     ix.set_deleted(np.zeros(n // 8 + 1, np.uint8))  # thawed
+    # a base destroyed before its view leaves an empty index behind, not a dangling one
+    v2 = ix.view()
     ix.close()
+    _, _, c2, _ = v2.search(Q[:4], k)
+    assert (c2 == 0).all()
+    v2.close()

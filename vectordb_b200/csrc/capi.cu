@@ -2,6 +2,7 @@
 // VecSearchExecutor::Search orchestration (engine/db/execution/vec_search_executor.cpp:833-935).
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -301,8 +302,22 @@ void eps_index_destroy(eps_index* h) {
   cudaStreamSynchronize(ix->stream);
   if (ix->view_of) {  // a view owns its seed set, stream and scratch only
     if (ix->d_init_ids) cudaFree(ix->d_init_ids);
-    --ix->view_of->n_views;
+    Index* base = ix->view_of;
+    --base->n_views;
+    base->views.erase(std::remove(base->views.begin(), base->views.end(), ix), base->views.end());
+  } else if (ix->detached_view) {
+    if (ix->d_init_ids) cudaFree(ix->d_init_ids);  // its base went first: nothing shared is left to release
   } else {
+    for (Index* v : ix->views) {  // base destroyed before its views: they become empty indexes instead of dangling
+      cudaStreamSynchronize(v->stream);
+      v->view_of = nullptr; v->detached_view = true;
+      v->d_vectors = nullptr; v->n_rows = 0; v->capacity = 0;
+      v->d_offsets = nullptr; v->d_nbrs = nullptr; v->d_ell = nullptr; v->n_indexed = 0; v->n_edges = 0;
+      v->d_deleted = nullptr; v->deleted_bytes = 0; v->any_deleted = false;
+      v->d_attrs = nullptr; v->attr_rows = 0;
+      for (auto& sc : v->str_cols) sc = eps::StrCol();
+    }
+    ix->views.clear();
     eps::free_graph(ix);
     if (ix->owns_vectors && ix->d_vectors) cudaFree(ix->d_vectors);
     if (ix->d_deleted) cudaFree(ix->d_deleted);
@@ -351,13 +366,14 @@ int eps_index_create_view(eps_index* base_h, eps_index** out) {
   if (e != cudaSuccess) { delete ix; return eps::fail(EPS_ERR_CUDA, cudaGetErrorString(e)); }
   for (auto& ev : ix->ev) cudaEventCreate(&ev);
   ++base->n_views;
+  base->views.push_back(ix);
   *out = reinterpret_cast<eps_index*>(ix);
   return EPS_OK;
 }
 
 // table, graph and segment mirrors of a view belong to its base; a base with live views is frozen
 static int check_mutable(const Index* ix) {
-  if (ix->view_of) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "a view is read-only");
+  if (ix->view_of || ix->detached_view) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "a view is read-only");
   if (ix->n_views > 0) return eps::fail(EPS_ERR_INVALID_ARGUMENT, "the index has live views: destroy them before modifying it");
   return EPS_OK;
 }

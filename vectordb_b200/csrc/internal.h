@@ -40,6 +40,8 @@ struct Index {
   bool owns_vectors = false;
   Index* view_of = nullptr;     // read-only view (eps_index_create_view): table, graph, segment mirrors belong to this index
   int n_views = 0;              // live views of this index; mutating entry points refuse while > 0
+  std::vector<Index*> views;    // the live views (detached when the base is destroyed first)
+  bool detached_view = false;   // a view whose base has been destroyed: holds no data any more
   int64_t n_rows = 0;           // rows mirrored so far (record_number_ snapshot)
   bool vec4 = false;            // dim % 4 == 0 and 16-B aligned base
 
