@@ -605,6 +605,9 @@ def main():
         A.set_mode(m)
         A.search(A.Qpool[0])
         rec = recall_of(A.truth, A.out_ids, a.k)
+        if m[0] == "graph" and a.width > 1:  # wide mode is not bit-reproducible: the gate is the worse of two passes
+            A.search(A.Qpool[0])
+            rec = min(rec, recall_of(A.truth, A.out_ids, a.k))
         timed_device_steps(m, a.warmup, 0)
         ms, stats = timed_device_steps(m, max(2, min(a.steps, 3)), a.warmup)
         qps = (1 if a.shard_rows else world) * a.batch * len(stats) / (ms / 1000.0)
@@ -811,6 +814,7 @@ def main():
         out["one_batch_at_a_time"] = {"value": units / (ms_serial / 1000.0), "unit": "queries/s", "ms_per_step": ms_serial / a.steps,
                                       "roofline_frac": roof["achieved"] * ms_dev / ms_serial / roof["peak"]}
         out["config"]["recall_per_lane"] = lanes_recall
+        out["config"][key_rec] = min([chosen[key_rec]] + lanes_recall)
         roof["timing"] = "%d steps over %d lanes (index + views); achieved = algorithmic bytes of the steps / region time" % (a.steps, n_lanes)
     out.update(extra)
     if misses is not None:
