@@ -47,6 +47,9 @@ def test_no_cpu_fallback_without_gpu():
     from vectordb_b200.index import pair_distances
     with pytest.raises(vectordb_b200.EpsError):
         pair_distances("l2", np.zeros((1, 4), np.float32), np.zeros((1, 4), np.float32))
+    import ctypes as C
+    h = C.c_void_p()
+    assert L.eps_index_create_view(None, C.byref(h)) != 0 and not h.value  # argument check before any device work
 
 
 def test_product_does_not_import_oracle():
