@@ -22,15 +22,18 @@
 //     cp.async.bulk + mbarrier complete_tx) issued by a single lane: no registers are held across the wait,
 //     every free ring slot is in flight at once, and the adjacency reads + visited-bitmap atomics of the NEXT
 //     candidates run while the rows of the previous ones land;
-//   * distances: 8-lane teams read the landed row and the query as float4 from shared memory, FMA, 3 shuffle
-//     steps; accepted keys (key < worst-in-queue) go to a small pending buffer that is merged into the sorted
-//     queue by a block-parallel rank-and-shift when it fills (or after every expansion in exact mode);
+//   * distances: warps 1-3 own the ring slots (slot s <-> warp 1 + s % 3); a warp waits on the mbarriers of its
+//     occupied slots, evaluates up to 8 landed rows with all 32 lanes on every row (float4 from shared memory, the
+//     lane's query chunk loaded once, 5 shuffle steps per row), refills its slots from the FIFO and keeps streaming
+//     while the FIFO has a backlog; accepted keys (key < worst-in-queue) go to a small pending buffer that is merged
+//     into the sorted queue by a block-parallel rank-and-shift when it fills (or after every expansion in exact mode);
 //   * adjacency: fixed-stride rows of 64 int32 ids (one 256-byte read from the vertex id; longer rows
 //     continue in the CSR); visited: one bitmap per in-flight query in global memory, atomicOr test-and-set,
-//     cleared by the CTA after the query like the reference clears its vector<bool> (:711-714).
+//     cleared by the CTA after the query like the reference clears its vector<bool> (:711-714) — on large tables
+//     only the words the query touched, from a log of its fresh ids.
 // exact mode (search width 1): one candidate per iteration, rows consumed and merged before the next pick —
 //   the visit order, results and distance-evaluation counts of the reference at IntraQueryThreads = 1.
-// wide mode (width W = 2/4/8): up to W candidates are picked per iteration from queue ∪ pending while the rows
+// wide mode (width W = 2..8): up to W candidates are picked per iteration from queue ∪ pending while the rows
 //   of the previous iteration are still in flight — the device analogue of IntraQueryThreads > 1; like that
 //   mode it is not bit-identical to the sequential order.
 #include <algorithm>
