@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       const int ncont = s_ncont;
       // -- D: merge the pending keys (every time in exact mode; when the buffer could overflow otherwise) --
       const bool merged = m > 0 && (a.exact || m > kPC - R);
-      // s_npend / s_head are bumped by the team phase below: no thread may get there before EVERY thread has taken
+      // s_npend / s_head are bumped by the consumer phase below: no thread may get there before EVERY thread has taken
       // the snapshot above (the merge's own barriers do that when there is a merge)
       if (merged) merge_pending(qa, pend, cs, pos, m, L, &s_npend, &s_cursor, ubits);
       else __syncthreads();
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kGsThreads, 7) graph_search_kernel(GSArgs a) {
       if (warp == 0) {
         int cnt = 0;
         if (ncont == 0) {
-          const int np = merged ? 0 : m;  // entries appended during this iteration's team phase are picked next time
+          const int np = merged ? 0 : m;  // entries appended during this iteration's consumer phase are picked next time
           int sp = s_cursor;
           unsigned long long pk[kPC / 32];
 #pragma unroll
