@@ -22,3 +22,45 @@ def test_reference_arm_prints_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_synthetic_tables_are_seeded_and_the_manifold_table_has_low_rank():
+    """bench.gen_table: same seed -> same bits; the "manifold" table = Gaussian blobs of sigma 0.1 in a 32-d latent
+    space embedded in R^d (+ small isotropic noise), i.e. its singular values collapse after the 32nd; the
+    "cluster" table is isotropic."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch
+    import bench
+    dev = torch.device("cpu")
+    a = bench.gen_table(3000, 96, "manifold", 42, dev, 16)
+    b = bench.gen_table(3000, 96, "manifold", 42, dev, 16)
+    assert torch.equal(a, b) and a.dtype == torch.float32 and tuple(a.shape) == (3000, 96)
+    s = np.linalg.svd((a - a.mean(0)).numpy(), compute_uv=False)
+    assert s[bench.LATENT_DIM - 1] > 10 * s[bench.LATENT_DIM], s[28:36]          # 32 directions carry the blobs
+    assert abs(s[-1] / np.sqrt(3000) - bench.LATENT_NOISE * bench.LATENT_SIGMA) < 2e-3  # the rest is the noise floor
+    c = bench.gen_table(3000, 96, "cluster", 42, dev, 16)
+    sc = np.linalg.svd((c - c.mean(0)).numpy(), compute_uv=False)
+    assert sc[40] > 0.5 * sc[20]                                                   # no low-rank structure beyond the 16 centres
+    q = bench.gen_queries(8, 96, "manifold", 43, dev, 16)
+    assert tuple(q.shape) == (8, 96) and float(torch.cdist(q, a).min(1).values.max()) < 1.5
+
+
+def test_classify_misses_separates_ties_from_real_losses():
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    ti = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]])
+    td = np.array([[0.1, 0.2, 0.3], [0.1, 0.2, 0.3], [0.1, 0.2, 0.3]], np.float32)
+    gi = np.array([[1, 2, 3], [4, 5, 60], [7, 8, 90]])
+    gd = np.array([[0.1, 0.2, 0.3], [0.1, 0.2, 0.3], [0.1, 0.2, 0.35]], np.float32)  # q1: same distance (tie), q2: worse
+    assert bench.classify_misses(ti, td, gi, gd, 3) == {"ties": 1, "real": 1}
+
+
+def test_measured_traffic_entries_point_at_committed_captures():
+    with open(os.path.join(ROOT, "profiles", "r02_measured_traffic.json")) as f:
+        d = json.load(f)
+    assert d["entries"]
+    for e in d["entries"]:
+        assert e["bytes_per_launch"] > 0 and {"rows", "dim", "dist", "batch", "L", "width"} <= set(e)
+        assert os.path.exists(os.path.join(ROOT, e["source"].split(" ")[0])), e["source"]
