@@ -540,6 +540,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def min_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
     hbm_peak, tf_peak, peak_src = measured_peaks()
     n_pool = a.warmup + a.steps
     A = Arena(a, a.dist, dev, local, rank, world, seed_shift=(rank if a.shard_rows else 0))
@@ -608,6 +614,9 @@ def main():
         if m[0] == "graph" and a.width > 1:  # wide mode is not bit-reproducible: the gate is the worse of two passes
             A.search(A.Qpool[0])
             rec = min(rec, recall_of(A.truth, A.out_ids, a.k))
+        # every rank builds its own graph (NN-descent is not deterministic): the gate is the worst rank's recall, so that
+        # all ranks stop the sweep at the same L and pick the same mode (their barriers must match)
+        rec = min_over_ranks(rec)
         timed_device_steps(m, a.warmup, 0)
         ms, stats = timed_device_steps(m, max(2, min(a.steps, 3)), a.warmup)
         qps = (1 if a.shard_rows else world) * a.batch * len(stats) / (ms / 1000.0)
