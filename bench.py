@@ -23,8 +23,10 @@ Workload.  Three synthetic 10M x 768 tables (random floats, seeded, generated on
     touches 75-95 % of the table for recall 0.99; graph search at L = 2048 finds 30 % of the neighbours): measured
     with the exact scan.
 `value` is the fastest mode (graph at the smallest L of the sweep that reaches the target, or the exact scan) with
-recall@10 >= 0.99 on the --dist table; the other two tables are measured in the same run (N = 1) and printed as the
-"cluster" / "uniform" records with their own recall, QPS and rooflines.
+recall@10 >= 0.99 on the --dist table; --extra-tables measures the other tables in the same run (N = 1) and prints
+them as "uniform" / "cluster" records with their own recall, QPS and rooflines.  The default run (3 min) carries
+the uniform record; `--extra-tables cluster,uniform` (5.7 min: one more graph build) adds the isotropic one, as in
+profiles/r02_bench_10Mx768_manifold_3lanes_*final.json.log.
 
 One "step" = one pass of the hot path over one batch of 1024 queries per GPU.  A step is timed with CUDA events on
 the index's launch stream, bracketed by barrier + synchronize, MAX over ranks.  `value` has the queries already
@@ -83,8 +85,9 @@ def parse():
     p.add_argument("--ctas", type=int, default=0, help="graph kernel: resident CTAs per SM (0 = auto)")
     p.add_argument("--knn-k", type=int, default=64)
     p.add_argument("--nnd-iters", type=int, default=14)
-    p.add_argument("--extra-tables", default="cluster,uniform", help="other SURVEY 8d tables measured in the same run at N=1 "
-                   "(cluster: graph + exact scan; uniform: exact scan, + graph with --uniform-graph); '' = none")
+    p.add_argument("--extra-tables", default="uniform", help="other SURVEY 8d tables measured in the same run at N=1 "
+                   "(uniform: exact scan, + graph with --uniform-graph; cluster: graph build + graph + exact scan, +2.7 min — "
+                   "the committed logs under profiles/ were made with 'cluster,uniform'); '' = none")
     p.add_argument("--uniform-graph", action="store_true", help="also build + search a graph on the iid-uniform table")
     p.add_argument("--shard-rows", action="store_true")
     p.add_argument("--recall-target", type=float, default=0.99)
