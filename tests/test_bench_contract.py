@@ -64,3 +64,18 @@ def test_measured_traffic_entries_point_at_committed_captures():
     for e in d["entries"]:
         assert e["bytes_per_launch"] > 0 and {"rows", "dim", "dist", "batch", "L", "width"} <= set(e)
         assert os.path.exists(os.path.join(ROOT, e["source"].split(" ")[0])), e["source"]
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: the driver launches the reference arm with torchrun like the GPU arm; rank 0 alone runs and prints the
+    line, the other ranks exit 0 without work."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29577", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--rows", "20000",
+                          "--dim", "32", "--batch", "64", "--steps", "2", "--warmup", "1", "--cpu-queries", "16"],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
